@@ -1,0 +1,796 @@
+// liboasr engine: weight store, workspace, the a8-a16 forward schedule and the C-ABI (include/oasr.h).
+#include "../../include/oasr.h"
+#include "gemm.cuh"
+#include "host_util.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace oasr;
+
+namespace {
+
+struct DevBuf {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  std::vector<int64_t> shape;
+  int dtype = OASR_DTYPE_F32;
+};
+
+int dev_alloc(void** p, size_t bytes, bool zero) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess)
+    return fail(OASR_ERR_CUDA, "cudaMalloc(" + std::to_string(bytes) + " bytes): " + cudaGetErrorString(e));
+  if (zero) {
+    e = cudaMemset(*p, 0, bytes);
+    if (e != cudaSuccess) return fail(OASR_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e));
+  }
+  return OASR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight preparation kernels (run once in oasr_finalize_weights)
+// ---------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+// conv weight [N][C][J] fp32 -> tap-major bf16 [N][J*k_pad + c], zero for c >= C
+__global__ void repack_conv_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int N, int C, int J,
+                                   int k_pad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * J * k_pad;
+  if (i >= total) return;
+  const int c = int(i % k_pad);
+  const int j = int((i / k_pad) % J);
+  const int n = int(i / ((long long)k_pad * J));
+  out[i] = c < C ? __float2bfloat16(in[((long long)n * C + c) * J + j]) : __float2bfloat16(0.f);
+}
+// layer-0 filter [512][1][10] -> [10][512] fp32
+__global__ void transpose_l0_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * K) out[(i % K) * C + (i / K)] = in[i];
+}
+// weight-norm(dim=2): per tap j, norm over (out, in) of v[:, :, j]
+__global__ void posnorm_kernel(const float* __restrict__ v, float* __restrict__ norms, long long rows, int J) {
+  const int j = blockIdx.x;
+  double s = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+    const double x = v[r * J + j];
+    s += x * x;
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norms[j] = (float)sqrt(sh[0]);
+}
+__global__ void posfold_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ norms,
+                               float* __restrict__ w, long long n, int J) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int j = int(i % J);
+    w[i] = v[i] * (g[j] / norms[j]);
+  }
+}
+
+inline unsigned blocks_for(long long n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
+
+struct LayerW {
+  float *attn_ln_g, *attn_ln_b, *ffn_ln_g, *ffn_ln_b;
+  __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+  float *bqkv, *bo, *b1, *b2;
+};
+
+}  // namespace
+
+struct OasrEngine {
+  OasrConfig cfg{};
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, DevBuf> raw;       // fp32 masters as loaded
+  std::vector<void*> owned;                // everything to cudaFree at destroy
+  int64_t launches = 0;
+
+  // finalised weights
+  float* fe0_w = nullptr;                  // [10][512]
+  std::vector<float*> fe_bias, fe_g, fe_b; // per FE layer
+  std::vector<__nv_bfloat16*> fe_w;        // layers >= 1, [512][k*512]
+  float *proj_ln_g = nullptr, *proj_ln_b = nullptr, *proj_bias = nullptr;
+  __nv_bfloat16* proj_w = nullptr;
+  __nv_bfloat16* pos_w = nullptr;          // [G][cg][K*k_pad]
+  float* pos_bias = nullptr;
+  int pos_kpad = 0;
+  std::vector<LayerW> layers;
+  float *final_ln_g = nullptr, *final_ln_b = nullptr, *ctc_bias = nullptr;
+  __nv_bfloat16* ctc_w = nullptr;
+
+  // workspace (grown on demand)
+  int ws_B = 0, ws_L = 0;
+  std::vector<void*> ws_owned;
+  float* wave = nullptr;       // [B, L]
+  double* wave_partials = nullptr;
+  __nv_bfloat16* fe_buf[2] = {nullptr, nullptr};
+  __nv_bfloat16* lnbuf = nullptr;   // [M, max(512, d)]
+  float* x = nullptr;               // [M, d]
+  __nv_bfloat16* xpad = nullptr;    // [B, T+K, d]
+  __nv_bfloat16* qkv = nullptr;     // [M, 3d]
+  __nv_bfloat16* att = nullptr;     // [M, d]
+  __nv_bfloat16* ffn = nullptr;     // [M, F]
+  unsigned long long* keys = nullptr;
+  int *n_samples_dev = nullptr, *n_frames_dev = nullptr;
+  int *frame_ids = nullptr, *out_ids = nullptr, *out_frames = nullptr, *out_lens = nullptr;
+  // pinned staging for n_samples / n_frames: a small ring so that the host can run ahead of the stream
+  static constexpr int STAGE_SLOTS = 8;
+  int32_t* h_stage = nullptr;       // [STAGE_SLOTS][2 * ws_B]
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {};
+  bool stage_used[STAGE_SLOTS] = {};
+  int stage_next = 0;
+  float* wave_raw = nullptr;        // [B, L] H2D landing buffer of oasr_transcribe_host
+  // shapes of the last forward (debug buffers)
+  int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
+  long long last_fe_pad = 0;
+};
+
+namespace {
+
+int fe_len(const OasrConfig& c, int64_t n, int upto) {
+  for (int i = 0; i < upto; ++i) n = n >= c.fe_kernel[i] ? (n - c.fe_kernel[i]) / c.fe_stride[i] + 1 : 0;
+  return (int)n;
+}
+inline long long fe_pad_rows(int t) { return ((long long)t + 3) & ~1ll; }  // even and >= t + 2
+
+int get_raw(OasrEngine* e, const std::string& name, std::initializer_list<int64_t> shape, float** out) {
+  auto it = e->raw.find(name);
+  if (it == e->raw.end()) return fail(OASR_ERR_STATE, "weight not loaded: " + name);
+  if (it->second.shape != std::vector<int64_t>(shape)) return fail(OASR_ERR_INVALID, "weight has wrong shape: " + name);
+  *out = reinterpret_cast<float*>(it->second.ptr);
+  return OASR_OK;
+}
+
+int alloc_owned(OasrEngine* e, void** p, size_t bytes, bool zero = false) {
+  OASR_TRY(dev_alloc(p, bytes, zero));
+  e->owned.push_back(*p);
+  return OASR_OK;
+}
+
+int to_bf16(OasrEngine* e, const float* src, long long n, __nv_bfloat16** dst) {
+  OASR_TRY(alloc_owned(e, reinterpret_cast<void**>(dst), (size_t)n * 2));
+  cast_bf16_kernel<<<blocks_for(n), 256>>>(src, *dst, n);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+void free_raw(OasrEngine* e, const std::string& name) {
+  auto it = e->raw.find(name);
+  if (it != e->raw.end()) {
+    cudaFree(it->second.ptr);
+    e->raw.erase(it);
+  }
+}
+
+int ensure_workspace(OasrEngine* e, int B, int L) {
+  if (B <= e->ws_B && L <= e->ws_L) return OASR_OK;
+  const int nB = std::max(B, e->ws_B), nL = std::max(L, e->ws_L);
+  OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (void* p : e->ws_owned) cudaFree(p);
+  e->ws_owned.clear();
+  e->ws_B = e->ws_L = 0;
+  const OasrConfig& c = e->cfg;
+  const int d = c.d_model, F = c.d_ffn;
+  auto A = [&](void** p, size_t bytes, bool zero) -> int {
+    OASR_TRY(dev_alloc(p, bytes, zero));
+    e->ws_owned.push_back(*p);
+    return OASR_OK;
+  };
+  const long long T0 = fe_len(c, nL, 1), T1 = fe_len(c, nL, 2);
+  const long long T = fe_len(c, nL, c.n_fe_layers);
+  const long long M = (long long)nB * std::max<long long>(T, 1);
+  OASR_TRY(A((void**)&e->wave, (size_t)nB * nL * 4, false));
+  OASR_TRY(A((void**)&e->wave_partials, (size_t)nB * WAVE_NORM_SLICES * 2 * 8, false));
+  OASR_TRY(A((void**)&e->fe_buf[0], (size_t)nB * fe_pad_rows((int)T0) * 512 * 2, true));
+  OASR_TRY(A((void**)&e->fe_buf[1], (size_t)nB * fe_pad_rows((int)T1) * 512 * 2, true));
+  OASR_TRY(A((void**)&e->lnbuf, (size_t)M * std::max(512, d) * 2, false));
+  OASR_TRY(A((void**)&e->x, (size_t)M * d * 4, false));
+  OASR_TRY(A((void**)&e->xpad, (size_t)nB * (T + c.pos_kernel) * d * 2, true));
+  OASR_TRY(A((void**)&e->qkv, (size_t)M * 3 * d * 2, false));
+  OASR_TRY(A((void**)&e->att, (size_t)M * d * 2, false));
+  OASR_TRY(A((void**)&e->ffn, (size_t)M * F * 2, false));
+  OASR_TRY(A((void**)&e->keys, (size_t)M * 8, true));
+  OASR_TRY(A((void**)&e->n_samples_dev, (size_t)nB * 4, true));
+  OASR_TRY(A((void**)&e->n_frames_dev, (size_t)nB * 4, true));
+  OASR_TRY(A((void**)&e->frame_ids, (size_t)M * 4, true));
+  OASR_TRY(A((void**)&e->out_ids, (size_t)M * 4, true));
+  OASR_TRY(A((void**)&e->out_frames, (size_t)M * 4, true));
+  OASR_TRY(A((void**)&e->out_lens, (size_t)nB * 4, true));
+  if (e->h_stage) cudaFreeHost(e->h_stage);
+  OASR_CUDA_CHECK(cudaMallocHost((void**)&e->h_stage, (size_t)OasrEngine::STAGE_SLOTS * nB * 2 * 4));
+  for (int i = 0; i < OasrEngine::STAGE_SLOTS; ++i) e->stage_used[i] = false;
+  OASR_TRY(A((void**)&e->wave_raw, (size_t)nB * nL * 4, false));
+  e->ws_B = nB;
+  e->ws_L = nL;
+  return OASR_OK;
+}
+
+// One FE conv layer (i >= 1) as an implicit GEMM with fused LayerNorm + GELU.
+int run_conv_layer(const void* in, int B, int T_in, long long in_pad_rows, int k, const void* w, const float* bias,
+                   const float* g, const float* b, void* out, long long out_pad_rows, cudaStream_t st) {
+  const int T_out = T_in >= k ? (T_in - k) / 2 + 1 : 0;
+  if (T_out == 0) return OASR_OK;
+  GemmArgs a;
+  a.A = in;
+  a.a_inner = 512;
+  a.taps = k;
+  a.k_pad = 512;
+  a.P = 2;
+  a.a_p_stride = 512;
+  a.a_pos_stride = 1024;
+  a.a_batch_stride = in_pad_rows * 512;
+  a.a_positions = T_out + (k - 1) / 2;
+  a.rows_per_batch = T_out;
+  a.batches = B;
+  a.W = w;
+  a.N = 512;
+  a.bias = bias;
+  a.ln_gamma = g;
+  a.ln_beta = b;
+  a.out = out;
+  a.ldo = 512;
+  a.out_batch_rows = out_pad_rows;
+  a.epilogue = EPI_LN_GELU_BF16;
+  return gemm_bf16_tcgen05(a, st);
+}
+
+int run_posconv(float* x, int B, int T, int d, int groups, int k, int k_pad, const void* w, const float* bias,
+                void* xpad, cudaStream_t st) {
+  const int cg = d / groups;
+  OASR_CUDA_CHECK(cudaMemsetAsync(xpad, 0, (size_t)B * (T + k) * d * 2, st));
+  OASR_TRY(pad_cast_bf16(x, B, T, d, k / 2, xpad, st));
+  GemmArgs a;
+  a.A = xpad;
+  a.a_inner = cg;
+  a.taps = k;
+  a.k_pad = k_pad;
+  a.P = 1;
+  a.a_pos_stride = d;
+  a.a_batch_stride = (long long)(T + k) * d;
+  a.a_group_stride = cg;
+  a.a_positions = T + k;
+  a.rows_per_batch = T;
+  a.batches = B;
+  a.groups = groups;
+  a.W = w;
+  a.N = cg;
+  a.bias = bias;
+  a.out = x;
+  a.ldo = d;
+  a.resid = x;
+  a.epilogue = EPI_F32_GELU_RESID;
+  return gemm_bf16_tcgen05(a, st);
+}
+
+int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const int32_t* n_samples_host, int B, int L,
+                 int flags, int stop_stage, float* hidden_out, cudaStream_t st) {
+  if (!e->finalized) return fail(OASR_ERR_STATE, "oasr_finalize_weights has not been called");
+  OASR_REQUIRE(wave_in && n_samples_host && B > 0 && L > 0, "forward: bad arguments");
+  const OasrConfig& c = e->cfg;
+  const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
+  OASR_TRY(ensure_workspace(e, B, L));
+  const int T = fe_len(c, L, c.n_fe_layers);
+  const long long M = (long long)B * T;
+  e->last_B = B;
+  e->last_L = L;
+  e->last_T = T;
+
+  const int slot = e->stage_next;
+  e->stage_next = (slot + 1) % OasrEngine::STAGE_SLOTS;
+  if (e->stage_used[slot]) OASR_CUDA_CHECK(cudaEventSynchronize(e->stage_ev[slot]));
+  int32_t* hs = e->h_stage + (size_t)slot * 2 * e->ws_B;
+  for (int b = 0; b < B; ++b) {
+    OASR_REQUIRE(n_samples_host[b] >= 0 && n_samples_host[b] <= L, "forward: n_samples out of range");
+    hs[b] = n_samples_host[b];
+    hs[B + b] = fe_len(c, n_samples_host[b], c.n_fe_layers);
+  }
+  OASR_CUDA_CHECK(cudaMemcpyAsync(e->n_samples_dev, hs, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  OASR_CUDA_CHECK(cudaMemcpyAsync(e->n_frames_dev, hs + B, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+  if (!e->stage_ev[slot]) OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->stage_ev[slot], cudaEventDisableTiming));
+  OASR_CUDA_CHECK(cudaEventRecord(e->stage_ev[slot], st));
+  e->stage_used[slot] = true;
+
+  // a8
+  const float* wv = wave_in;
+  long long wv_stride = wave_stride;
+  if (!(flags & OASR_FLAG_INPUT_NORMALISED)) {
+    OASR_TRY(wave_norm(wave_in, e->wave, e->n_samples_dev, B, L, wave_stride, L, e->wave_partials, st));
+    e->launches += 2;
+    wv = e->wave;
+    wv_stride = L;
+  }
+  // a9
+  int t_prev = fe_len(c, L, 1);
+  long long pad_prev = fe_pad_rows(t_prev);
+  OASR_TRY(fe_layer0(wv, wv_stride, B, L, e->fe0_w, e->fe_bias[0], e->fe_g[0], e->fe_b[0], e->fe_buf[0],
+                     pad_prev * 512, t_prev, st));
+  e->launches += 1;
+  int cur = 0;
+  // a10-a11
+  for (int i = 1; i < c.n_fe_layers; ++i) {
+    const int t_out = t_prev >= c.fe_kernel[i] ? (t_prev - c.fe_kernel[i]) / 2 + 1 : 0;
+    const long long pad_out = fe_pad_rows(t_out);
+    OASR_TRY(run_conv_layer(e->fe_buf[cur], B, t_prev, pad_prev, c.fe_kernel[i], e->fe_w[i], e->fe_bias[i],
+                            e->fe_g[i], e->fe_b[i], e->fe_buf[cur ^ 1], pad_out, st));
+    e->launches += 1;
+    cur ^= 1;
+    t_prev = t_out;
+    pad_prev = pad_out;
+  }
+  e->last_fe_idx = cur;
+  e->last_fe_pad = pad_prev;
+  if (stop_stage == 1 || T == 0) return OASR_OK;
+
+  // a12
+  OASR_TRY(layernorm_rows(e->fe_buf[cur], 1, pad_prev * 512, B, T, 512, e->proj_ln_g, e->proj_ln_b, e->lnbuf, nullptr, st));
+  {
+    GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, 512, 512, e->proj_w, d);
+    a.bias = e->proj_bias;
+    a.out = e->x;
+    a.ldo = d;
+    a.n_valid = e->n_frames_dev;
+    a.frames_per_seq = T;
+    a.epilogue = EPI_F32;
+    OASR_TRY(gemm_bf16_tcgen05(a, st));
+  }
+  e->launches += 2;
+  if (stop_stage == 2) return OASR_OK;
+
+  // a13
+  OASR_TRY(run_posconv(e->x, B, T, d, c.pos_groups, c.pos_kernel, e->pos_kpad, e->pos_w, e->pos_bias, e->xpad, st));
+  e->launches += 3;
+  if (stop_stage == 3) return OASR_OK;
+
+  // a14
+  const float scale = 1.0f / sqrtf((float)hd);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerW& w = e->layers[l];
+    OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.attn_ln_g, w.attn_ln_b, e->lnbuf, nullptr, st));
+    {
+      GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.wqkv, 3 * d);
+      a.bias = w.bqkv;
+      a.out = e->qkv;
+      a.ldo = 3 * d;
+      a.epilogue = EPI_BF16;
+      OASR_TRY(gemm_bf16_tcgen05(a, st));
+    }
+    OASR_TRY(attention_bf16(e->qkv, e->att, e->n_frames_dev, B, T, H, hd, scale, st));
+    {
+      GemmArgs a = GemmArgs::plain(e->att, (int)M, d, d, w.wo, d);
+      a.bias = w.bo;
+      a.out = e->x;
+      a.ldo = d;
+      a.resid = e->x;
+      a.epilogue = EPI_F32_RESID;
+      OASR_TRY(gemm_bf16_tcgen05(a, st));
+    }
+    OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.ffn_ln_g, w.ffn_ln_b, e->lnbuf, nullptr, st));
+    {
+      GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.w1, F);
+      a.bias = w.b1;
+      a.out = e->ffn;
+      a.ldo = F;
+      a.epilogue = EPI_BF16_GELU;
+      OASR_TRY(gemm_bf16_tcgen05(a, st));
+    }
+    {
+      GemmArgs a = GemmArgs::plain(e->ffn, (int)M, F, F, w.w2, d);
+      a.bias = w.b2;
+      a.out = e->x;
+      a.ldo = d;
+      a.resid = e->x;
+      a.epilogue = EPI_F32_RESID;
+      OASR_TRY(gemm_bf16_tcgen05(a, st));
+    }
+    e->launches += 7;
+    if (stop_stage == 4 + l) return OASR_OK;
+  }
+  OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
+  // a15: logits stay in TMEM; only a packed (max, index) key per frame reaches HBM
+  OASR_CUDA_CHECK(cudaMemsetAsync(e->keys, 0, (size_t)M * 8, st));
+  {
+    GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, e->ctc_w, c.vocab);
+    a.bias = e->ctc_bias;
+    a.argmax = e->keys;
+    a.epilogue = EPI_ARGMAX;
+    OASR_TRY(gemm_bf16_tcgen05(a, st));
+  }
+  // a16
+  OASR_TRY(ctc_decode(e->keys, e->n_frames_dev, B, T, c.blank_id, e->frame_ids, e->out_ids, e->out_frames, e->out_lens, st));
+  e->launches += 4;
+  return OASR_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* oasr_version(void) { return "oasr-b200 0.1.0 (sm_100a)"; }
+const char* oasr_last_error(void) { return last_error_cstr(); }
+
+int32_t oasr_feature_length(const OasrConfig* cfg, int64_t n_samples) {
+  if (!cfg) return 0;
+  return fe_len(*cfg, n_samples, cfg->n_fe_layers);
+}
+
+int oasr_create(const OasrConfig* cfg, OasrHandle* out) {
+  OASR_REQUIRE(cfg && out, "oasr_create: null argument");
+  *out = nullptr;
+  const OasrConfig& c = *cfg;
+  if (c.fe_dim != 512 || c.n_fe_layers < 2 || c.n_fe_layers > 8 || c.fe_kernel[0] != 10 || c.fe_stride[0] != 5)
+    return fail(OASR_ERR_UNSUPPORTED, "feature extractor must be 512 channels with a (k=10, s=5) first layer");
+  for (int i = 1; i < c.n_fe_layers; ++i)
+    if (c.fe_stride[i] != 2 || (c.fe_kernel[i] != 2 && c.fe_kernel[i] != 3))
+      return fail(OASR_ERR_UNSUPPORTED, "feature extractor layers >= 1 must be stride 2 with kernel 2 or 3");
+  OASR_REQUIRE(c.d_model > 0 && c.n_heads > 0 && c.d_model % c.n_heads == 0, "d_model must be divisible by n_heads");
+  const int hd = c.d_model / c.n_heads;
+  if (hd % 16 != 0 || hd > 128) return fail(OASR_ERR_UNSUPPORTED, "head_dim must be a multiple of 16 and <= 128");
+  if (c.d_model % 64 != 0 || c.d_model > 2048 || c.d_ffn % 64 != 0)
+    return fail(OASR_ERR_UNSUPPORTED, "d_model (<= 2048) and d_ffn must be multiples of 64");
+  OASR_REQUIRE(c.pos_groups > 0 && c.d_model % c.pos_groups == 0, "d_model must be divisible by pos_groups");
+  const int cg = c.d_model / c.pos_groups;
+  if (cg % 16 != 0 || cg > 128) return fail(OASR_ERR_UNSUPPORTED, "pos-conv group width must be a multiple of 16 and <= 128");
+  OASR_REQUIRE(c.pos_kernel >= 2 && c.pos_kernel % 2 == 0, "pos_kernel must be even");
+  OASR_REQUIRE(c.vocab > 0 && c.n_layers >= 0 && c.blank_id >= 0 && c.blank_id < c.vocab, "bad vocab / layers / blank");
+  int dev = 0;
+  OASR_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  OASR_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return fail(OASR_ERR_UNSUPPORTED, std::string("liboasr is built for sm_100a only; device is ") + prop.name);
+  OasrEngine* e = new OasrEngine();
+  e->cfg = c;
+  e->device = dev;
+  *out = e;
+  return OASR_OK;
+}
+
+void oasr_destroy(OasrHandle h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  for (auto& kv : h->raw) cudaFree(kv.second.ptr);
+  for (void* p : h->owned) cudaFree(p);
+  for (void* p : h->ws_owned) cudaFree(p);
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  for (cudaEvent_t ev : h->stage_ev) if (ev) cudaEventDestroy(ev);
+  delete h;
+}
+
+int oasr_load_weight(OasrHandle h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
+  OASR_REQUIRE(h && name && data && shape && ndim >= 1 && ndim <= 4, "oasr_load_weight: bad arguments");
+  if (h->finalized) return fail(OASR_ERR_STATE, "weights already finalised");
+  OASR_REQUIRE(dtype == OASR_DTYPE_F32 || dtype == OASR_DTYPE_BF16, "oasr_load_weight: dtype must be f32 or bf16");
+  long long n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    OASR_REQUIRE(shape[i] > 0, "oasr_load_weight: non-positive extent");
+    n *= shape[i];
+  }
+  free_raw(h, name);
+  DevBuf b;
+  b.bytes = (size_t)n * 4;
+  b.shape.assign(shape, shape + ndim);
+  OASR_TRY(dev_alloc(&b.ptr, b.bytes, false));
+  if (dtype == OASR_DTYPE_F32) {
+    OASR_CUDA_CHECK(cudaMemcpy(b.ptr, data, b.bytes, cudaMemcpyDefault));
+  } else {
+    // widen bf16 -> fp32 master through a temporary device copy
+    void* tmp = nullptr;
+    OASR_TRY(dev_alloc(&tmp, (size_t)n * 2, false));
+    cudaError_t ce = cudaMemcpy(tmp, data, (size_t)n * 2, cudaMemcpyDefault);
+    if (ce == cudaSuccess) {
+      std::vector<uint16_t> hb((size_t)n);
+      std::vector<float> hf((size_t)n);
+      ce = cudaMemcpy(hb.data(), tmp, (size_t)n * 2, cudaMemcpyDeviceToHost);
+      for (long long i = 0; i < n && ce == cudaSuccess; ++i) {
+        uint32_t u = (uint32_t)hb[(size_t)i] << 16;
+        memcpy(&hf[(size_t)i], &u, 4);
+      }
+      if (ce == cudaSuccess) ce = cudaMemcpy(b.ptr, hf.data(), b.bytes, cudaMemcpyHostToDevice);
+    }
+    cudaFree(tmp);
+    if (ce != cudaSuccess) {
+      cudaFree(b.ptr);
+      return fail(OASR_ERR_CUDA, std::string("oasr_load_weight copy: ") + cudaGetErrorString(ce));
+    }
+  }
+  h->raw[name] = b;
+  return OASR_OK;
+}
+
+int oasr_finalize_weights(OasrHandle h) {
+  OASR_REQUIRE(h, "oasr_finalize_weights: null handle");
+  if (h->finalized) return OASR_OK;
+  OasrEngine* e = h;
+  const OasrConfig& c = e->cfg;
+  const int d = c.d_model, F = c.d_ffn;
+  // --- feature extractor
+  e->fe_bias.assign(c.n_fe_layers, nullptr);
+  e->fe_g.assign(c.n_fe_layers, nullptr);
+  e->fe_b.assign(c.n_fe_layers, nullptr);
+  e->fe_w.assign(c.n_fe_layers, nullptr);
+  for (int i = 0; i < c.n_fe_layers; ++i) {
+    const std::string p = "fe." + std::to_string(i) + ".";
+    float* w = nullptr;
+    const int cin = i == 0 ? 1 : 512;
+    OASR_TRY(get_raw(e, p + "conv.weight", {512, cin, c.fe_kernel[i]}, &w));
+    OASR_TRY(get_raw(e, p + "conv.bias", {512}, &e->fe_bias[i]));
+    OASR_TRY(get_raw(e, p + "ln.weight", {512}, &e->fe_g[i]));
+    OASR_TRY(get_raw(e, p + "ln.bias", {512}, &e->fe_b[i]));
+    if (i == 0) {
+      OASR_TRY(alloc_owned(e, (void**)&e->fe0_w, 10 * 512 * 4));
+      transpose_l0_kernel<<<blocks_for(5120), 256>>>(w, e->fe0_w, 512, 10);
+    } else {
+      const long long n = 512ll * c.fe_kernel[i] * 512;
+      OASR_TRY(alloc_owned(e, (void**)&e->fe_w[i], (size_t)n * 2));
+      repack_conv_kernel<<<blocks_for(n), 256>>>(w, e->fe_w[i], 512, 512, c.fe_kernel[i], 512);
+    }
+    OASR_CUDA_CHECK(cudaGetLastError());
+  }
+  // --- projection
+  {
+    float* w = nullptr;
+    OASR_TRY(get_raw(e, "proj.ln.weight", {512}, &e->proj_ln_g));
+    OASR_TRY(get_raw(e, "proj.ln.bias", {512}, &e->proj_ln_b));
+    OASR_TRY(get_raw(e, "proj.linear.weight", {d, 512}, &w));
+    OASR_TRY(get_raw(e, "proj.linear.bias", {d}, &e->proj_bias));
+    OASR_TRY(to_bf16(e, w, (long long)d * 512, &e->proj_w));
+  }
+  // --- positional conv: fold weight-norm, repack per group tap-major, pad each tap to k_pad columns
+  {
+    const int G = c.pos_groups, cg = d / G, K = c.pos_kernel;
+    float *g = nullptr, *v = nullptr;
+    OASR_TRY(get_raw(e, "pos.weight_g", {1, 1, K}, &g));
+    OASR_TRY(get_raw(e, "pos.weight_v", {d, cg, K}, &v));
+    OASR_TRY(get_raw(e, "pos.bias", {d}, &e->pos_bias));
+    float *norms = nullptr, *folded = nullptr;
+    const long long n = (long long)d * cg * K;
+    OASR_TRY(dev_alloc((void**)&norms, (size_t)K * 4, false));
+    OASR_TRY(dev_alloc((void**)&folded, (size_t)n * 4, false));
+    posnorm_kernel<<<K, 256>>>(v, norms, (long long)d * cg, K);
+    posfold_kernel<<<blocks_for(n), 256>>>(v, g, norms, folded, n, K);
+    e->pos_kpad = ((cg + 63) / 64) * 64;
+    const long long nw = (long long)d * K * e->pos_kpad;
+    OASR_TRY(alloc_owned(e, (void**)&e->pos_w, (size_t)nw * 2));
+    // [d][cg][K] viewed as N=d rows: row n = g*cg + n_in_group, so one launch covers all groups
+    repack_conv_kernel<<<blocks_for(nw), 256>>>(folded, e->pos_w, d, cg, K, e->pos_kpad);
+    OASR_CUDA_CHECK(cudaGetLastError());
+    OASR_CUDA_CHECK(cudaDeviceSynchronize());
+    cudaFree(norms);
+    cudaFree(folded);
+  }
+  // --- encoder layers
+  e->layers.resize(c.n_layers);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const std::string p = "enc." + std::to_string(l) + ".";
+    LayerW& w = e->layers[l];
+    float *wq, *wk, *wv, *wo, *w1, *w2, *bq, *bk, *bv;
+    OASR_TRY(get_raw(e, p + "attn_ln.weight", {d}, &w.attn_ln_g));
+    OASR_TRY(get_raw(e, p + "attn_ln.bias", {d}, &w.attn_ln_b));
+    OASR_TRY(get_raw(e, p + "ffn_ln.weight", {d}, &w.ffn_ln_g));
+    OASR_TRY(get_raw(e, p + "ffn_ln.bias", {d}, &w.ffn_ln_b));
+    OASR_TRY(get_raw(e, p + "q.weight", {d, d}, &wq));
+    OASR_TRY(get_raw(e, p + "k.weight", {d, d}, &wk));
+    OASR_TRY(get_raw(e, p + "v.weight", {d, d}, &wv));
+    OASR_TRY(get_raw(e, p + "o.weight", {d, d}, &wo));
+    OASR_TRY(get_raw(e, p + "q.bias", {d}, &bq));
+    OASR_TRY(get_raw(e, p + "k.bias", {d}, &bk));
+    OASR_TRY(get_raw(e, p + "v.bias", {d}, &bv));
+    OASR_TRY(get_raw(e, p + "o.bias", {d}, &w.bo));
+    OASR_TRY(get_raw(e, p + "ffn1.weight", {F, d}, &w1));
+    OASR_TRY(get_raw(e, p + "ffn1.bias", {F}, &w.b1));
+    OASR_TRY(get_raw(e, p + "ffn2.weight", {d, F}, &w2));
+    OASR_TRY(get_raw(e, p + "ffn2.bias", {d}, &w.b2));
+    const long long dd = (long long)d * d;
+    OASR_TRY(alloc_owned(e, (void**)&w.wqkv, (size_t)dd * 3 * 2));
+    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wq, w.wqkv, dd);
+    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wk, w.wqkv + dd, dd);
+    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wv, w.wqkv + 2 * dd, dd);
+    OASR_TRY(alloc_owned(e, (void**)&w.bqkv, (size_t)d * 3 * 4));
+    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv, bq, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + d, bk, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + 2 * d, bv, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    OASR_TRY(to_bf16(e, wo, dd, &w.wo));
+    OASR_TRY(to_bf16(e, w1, (long long)F * d, &w.w1));
+    OASR_TRY(to_bf16(e, w2, (long long)F * d, &w.w2));
+    OASR_CUDA_CHECK(cudaDeviceSynchronize());
+    for (const char* n : {"q.weight", "k.weight", "v.weight", "o.weight", "ffn1.weight", "ffn2.weight"}) free_raw(e, p + n);
+  }
+  // --- head
+  {
+    float* w = nullptr;
+    OASR_TRY(get_raw(e, "final_ln.weight", {d}, &e->final_ln_g));
+    OASR_TRY(get_raw(e, "final_ln.bias", {d}, &e->final_ln_b));
+    OASR_TRY(get_raw(e, "ctc.weight", {c.vocab, d}, &w));
+    OASR_TRY(get_raw(e, "ctc.bias", {c.vocab}, &e->ctc_bias));
+    OASR_TRY(to_bf16(e, w, (long long)c.vocab * d, &e->ctc_w));
+  }
+  OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (const char* n : {"proj.linear.weight", "pos.weight_v", "ctc.weight"}) free_raw(e, n);
+  for (int i = 1; i < c.n_fe_layers; ++i) free_raw(e, "fe." + std::to_string(i) + ".conv.weight");
+  e->finalized = true;
+  return OASR_OK;
+}
+
+int oasr_forward_ctc(OasrHandle h, const float* wave_dev, int64_t wave_stride, const int32_t* n_samples_host,
+                     int32_t B, int32_t L, int32_t flags, int32_t* frame_ids_dev, float* hidden_dev,
+                     int32_t* out_ids_dev, int32_t* out_frames_dev, int32_t* out_lens_dev, OasrStream stream) {
+  OASR_REQUIRE(h, "oasr_forward_ctc: null handle");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  OASR_TRY(forward_impl(h, wave_dev, wave_stride > 0 ? wave_stride : L, n_samples_host, B, L, flags, 0, hidden_dev, st));
+  const size_t n = (size_t)B * h->last_T * 4;
+  if (h->last_T > 0) {
+    if (frame_ids_dev) OASR_CUDA_CHECK(cudaMemcpyAsync(frame_ids_dev, h->frame_ids, n, cudaMemcpyDeviceToDevice, st));
+    if (out_ids_dev) OASR_CUDA_CHECK(cudaMemcpyAsync(out_ids_dev, h->out_ids, n, cudaMemcpyDeviceToDevice, st));
+    if (out_frames_dev) OASR_CUDA_CHECK(cudaMemcpyAsync(out_frames_dev, h->out_frames, n, cudaMemcpyDeviceToDevice, st));
+    if (out_lens_dev) OASR_CUDA_CHECK(cudaMemcpyAsync(out_lens_dev, h->out_lens, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (out_lens_dev) {
+    OASR_CUDA_CHECK(cudaMemsetAsync(out_lens_dev, 0, (size_t)B * 4, st));
+  }
+  return OASR_OK;
+}
+
+int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stride, const int32_t* n_samples_host,
+                         int32_t B, int32_t L, int32_t flags, int32_t* out_ids_host, int32_t* out_frames_host,
+                         int32_t* out_lens_host, int32_t* frame_ids_host, OasrStream stream) {
+  OASR_REQUIRE(h && wave_host && out_lens_host, "oasr_transcribe_host: null argument");
+  OASR_REQUIRE(B > 0 && L > 0, "oasr_transcribe_host: empty batch");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  OASR_TRY(ensure_workspace(h, B, L));
+  const int64_t ws = wave_stride > 0 ? wave_stride : L;
+  float* dst = h->wave_raw;
+  void* tmp = nullptr;
+  cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)L * 4, wave_host, (size_t)ws * 4, (size_t)L * 4, B,
+                                     cudaMemcpyHostToDevice, st);
+  int rc = OASR_OK;
+  if (ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("H2D waveform: ") + cudaGetErrorString(ce));
+  if (rc == OASR_OK) rc = forward_impl(h, dst, L, n_samples_host, B, L, flags, 0, nullptr, st);
+  const size_t n = (size_t)B * h->last_T * 4;
+  if (rc == OASR_OK && h->last_T > 0) {
+    if (out_ids_host) ce = cudaMemcpyAsync(out_ids_host, h->out_ids, n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && out_frames_host) ce = cudaMemcpyAsync(out_frames_host, h->out_frames, n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess && frame_ids_host) ce = cudaMemcpyAsync(frame_ids_host, h->frame_ids, n, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(out_lens_host, h->out_lens, (size_t)B * 4, cudaMemcpyDeviceToHost, st);
+    if (ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("D2H ids: ") + cudaGetErrorString(ce));
+  } else if (rc == OASR_OK) {
+    memset(out_lens_host, 0, (size_t)B * 4);
+  }
+  ce = cudaStreamSynchronize(st);
+  if (rc == OASR_OK && ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(ce));
+  if (tmp) cudaFree(tmp);
+  return rc;
+}
+
+int oasr_debug_forward(OasrHandle h, const float* wave_dev, int64_t wave_stride, const int32_t* n_samples_host,
+                       int32_t B, int32_t L, int32_t flags, int32_t stop_stage, OasrStream stream) {
+  OASR_REQUIRE(h, "oasr_debug_forward: null handle");
+  return forward_impl(h, wave_dev, wave_stride > 0 ? wave_stride : L, n_samples_host, B, L, flags, stop_stage, nullptr,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_debug_buffer(OasrHandle h, const char* name, void** dev_ptr, int64_t* shape4, int32_t* dtype) {
+  OASR_REQUIRE(h && name && dev_ptr && shape4 && dtype, "oasr_debug_buffer: null argument");
+  const std::string n(name);
+  for (int i = 0; i < 4; ++i) shape4[i] = 0;
+  if (n == "fe") {
+    *dev_ptr = h->fe_buf[h->last_fe_idx];
+    shape4[0] = h->last_B; shape4[1] = h->last_fe_pad; shape4[2] = 512;
+    *dtype = OASR_DTYPE_BF16;
+  } else if (n == "x") {
+    *dev_ptr = h->x;
+    shape4[0] = (int64_t)h->last_B * h->last_T; shape4[1] = h->cfg.d_model;
+    *dtype = OASR_DTYPE_F32;
+  } else if (n == "wave") {
+    *dev_ptr = h->wave;
+    shape4[0] = h->last_B; shape4[1] = h->last_L;
+    *dtype = OASR_DTYPE_F32;
+  } else if (n == "att") {
+    *dev_ptr = h->att;
+    shape4[0] = (int64_t)h->last_B * h->last_T; shape4[1] = h->cfg.d_model;
+    *dtype = OASR_DTYPE_BF16;
+  } else if (n == "qkv") {
+    *dev_ptr = h->qkv;
+    shape4[0] = (int64_t)h->last_B * h->last_T; shape4[1] = 3 * h->cfg.d_model;
+    *dtype = OASR_DTYPE_BF16;
+  } else {
+    return fail(OASR_ERR_INVALID, "unknown debug buffer: " + n);
+  }
+  return OASR_OK;
+}
+
+int64_t oasr_launch_count(OasrHandle h) { return h ? h->launches : 0; }
+
+// ---- per-stage entry points ---------------------------------------------------------------------------
+int oasr_wave_norm(const float* in, float* out, const int32_t* n_samples_dev, int32_t B, int32_t L, OasrStream stream) {
+  double* partials = nullptr;
+  OASR_TRY(dev_alloc((void**)&partials, (size_t)B * WAVE_NORM_SLICES * 16, false));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = wave_norm(in, out, n_samples_dev, B, L, L, L, partials, st);
+  cudaStreamSynchronize(st);
+  cudaFree(partials);
+  return rc;
+}
+
+int oasr_fe_layer0(const float* wave, int32_t B, int32_t L, const float* w_10x512, const float* bias, const float* gamma,
+                   const float* beta, void* out_bf16, OasrStream stream) {
+  const int T0 = L >= 10 ? (L - 10) / 5 + 1 : 0;
+  return fe_layer0(wave, L, B, L, w_10x512, bias, gamma, beta, out_bf16, (long long)T0 * 512, T0,
+                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_conv_ln_gelu(const void* in_bf16, int32_t B, int32_t L_in, int32_t L_in_pad, int32_t k, const void* w_bf16,
+                      const float* bias, const float* gamma, const float* beta, void* out_bf16, OasrStream stream) {
+  OASR_REQUIRE(k == 2 || k == 3, "conv_ln_gelu: kernel must be 2 or 3");
+  OASR_REQUIRE(L_in_pad % 2 == 0 && L_in_pad >= L_in + 2, "conv_ln_gelu: L_in_pad must be even and >= L_in + 2");
+  const int T_out = L_in >= k ? (L_in - k) / 2 + 1 : 0;
+  return run_conv_layer(in_bf16, B, L_in, L_in_pad, k, w_bf16, bias, gamma, beta, out_bf16, T_out,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_layernorm(const void* in, int32_t in_is_bf16, int64_t rows, int32_t D, const float* gamma, const float* beta,
+                   void* out_bf16, float* out_f32, OasrStream stream) {
+  return layernorm_rows(in, in_is_bf16, 0, 1, (int)rows, D, gamma, beta, out_bf16, out_f32,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_gemm(const void* A_bf16, const void* W_bf16, const float* bias, int32_t M, int32_t N, int32_t K,
+              int32_t epilogue, void* out, int32_t ldo, const float* resid, const float* ln_gamma,
+              const float* ln_beta, uint64_t* argmax_keys, OasrStream stream) {
+  GemmArgs a = GemmArgs::plain(A_bf16, M, K, K, W_bf16, N);
+  a.bias = bias;
+  a.out = out;
+  a.ldo = ldo;
+  a.resid = resid;
+  a.ln_gamma = ln_gamma;
+  a.ln_beta = ln_beta;
+  a.argmax = reinterpret_cast<unsigned long long*>(argmax_keys);
+  a.epilogue = epilogue;
+  return gemm_bf16_tcgen05(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_posconv(float* x, int32_t B, int32_t T, int32_t d, int32_t groups, int32_t k, const void* w_bf16,
+                 const float* bias, void* scratch_bf16, OasrStream stream) {
+  OASR_REQUIRE(x && w_bf16 && bias && scratch_bf16 && groups > 0 && d % groups == 0, "posconv: bad arguments");
+  const int cg = d / groups;
+  OASR_REQUIRE(cg % 16 == 0 && cg <= 128 && k % 2 == 0, "posconv: unsupported group width / kernel");
+  return run_posconv(x, B, T, d, groups, k, ((cg + 63) / 64) * 64, w_bf16, bias, scratch_bf16,
+                     reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_attention(const void* qkv_bf16, void* out_bf16, const int32_t* n_frames_dev, int32_t B, int32_t T, int32_t H,
+                   int32_t hd, float scale, OasrStream stream) {
+  return attention_bf16(qkv_bf16, out_bf16, n_frames_dev, B, T, H, hd, scale, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_ctc_decode(const uint64_t* keys, const int32_t* n_frames_dev, int32_t B, int32_t T, int32_t blank,
+                    int32_t* frame_ids, int32_t* out_ids, int32_t* out_frames, int32_t* out_lens, OasrStream stream) {
+  return ctc_decode(reinterpret_cast<const unsigned long long*>(keys), n_frames_dev, B, T, blank, frame_ids, out_ids,
+                    out_frames, out_lens, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int oasr_ctc_collapse(const int32_t* frame_ids, const int32_t* n_frames_dev, int32_t B, int32_t T, int32_t blank,
+                      int32_t* out_ids, int32_t* out_frames, int32_t* out_lens, OasrStream stream) {
+  return ctc_collapse(frame_ids, n_frames_dev, B, T, blank, out_ids, out_frames, out_lens,
+                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,523 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem ring -> tcgen05.mma
+// (accumulators in TMEM, double buffered) -> tcgen05.ld epilogue with fused bias / GELU / residual /
+// LayerNorm+GELU / arg-max.  One CTA per SM, 384 threads:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      MMA issuer   (one elected lane)
+//   warp 2      TMEM allocator
+//   warp 3      idle
+//   warps 4-11  epilogue: warp w owns TMEM lanes [32*(w%4), +32) and column half (w-4)/4 of the tile
+// Used for: FE conv layers 1-6 (implicit GEMM over overlapping rows), feature projection, QKV, out-proj,
+// FFN1, FFN2 and the CTC head.
+#include "gemm.cuh"
+#include "host_util.h"
+#include "ptx.cuh"
+
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace oasr {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // one 128-byte swizzle atom of bf16
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+
+struct GemmKernelParams {
+  int rows_per_batch, batches, groups, N;
+  int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
+  int kb_per_tap, P;       // k-block -> (tap, column block); tap -> (parity, position offset)
+  int umma_n;              // N of one tcgen05.mma (<= 256, multiple of 16)
+  int b_box_rows;          // rows of W fetched per TMA box
+  uint32_t stage_tx_bytes; // bytes landing on a full barrier per stage
+  int ldo;
+  long long out_batch_rows;
+  void* out;
+  const float* bias;
+  const float* resid;
+  const float* ln_gamma;
+  const float* ln_beta;
+  unsigned long long* argmax;
+  const int* n_valid;
+  int frames_per_seq;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
+  static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
+  static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
+  static constexpr int UMMA_N = BN > 256 ? 256 : BN;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+};
+
+struct TileCoord {
+  int n_tile, m0, b, g;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  t.m0 = (mt % p.m_tiles_per_batch) * BM;
+  mt /= p.m_tiles_per_batch;
+  t.b = mt % p.batches;
+  t.g = mt / p.batches;
+  return t;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const GemmKernelParams p) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bar_base = smem + C::STAGES * C::STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty = full + C::STAGES;
+  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* red1 = reinterpret_cast<float*>(bar_base + 256);  // [2][128] LN partial sums
+  float* red2 = red1 + 256;                                // [2][128]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sA = smem + s * C::STAGE_BYTES;
+          uint8_t* sB = sA + C::A_BYTES;
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * BK;
+          mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
+          tma_load_5d(sA, &tmA, &full[s], c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
+          for (int j = 0; j < BN && j < p.N; j += p.b_box_rows)
+            tma_load_3d(sB + j * (BK * 2), &tmB, &full[s], kb * BK, t.n_tile * BN + j, t.g);
+          if (++s == C::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, p.umma_n, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int as = 0;
+      uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
+#pragma unroll
+            for (int j = 0; j < BN && j < p.N; j += 256) {
+              const uint64_t bdesc = make_smem_desc(b_addr + j * (BK * 2) + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
+              umma_ss(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          if (++s == C::STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete
+        if (C::ACC_STAGES == 2) {
+          as ^= 1;
+          if (as == 0) aph ^= 1;
+        } else {
+          aph ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;          // TMEM lane quarter this warp may touch
+    const int half = (warp - 4) >> 2;
+    constexpr int HALF_N = BN / 2;
+    int as = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int row_in_tile = q * 32 + lane;
+      const int r = tc.m0 + row_in_tile;
+      const bool row_ok = r < p.rows_per_batch;
+      const long long out_row = (long long)tc.b * p.out_batch_rows + r;
+      const int n_base = tc.n_tile * BN + half * HALF_N;   // column within the group
+      const int gcol = tc.g * p.N;                         // first output column of the group
+      const float* bias_g = p.bias ? p.bias + gcol : nullptr;
+      const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * HALF_N;
+
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+
+      if constexpr (EPI == EPI_LN_GELU_BF16) {
+        // LayerNorm over the 512 channels of the row: 3 passes over TMEM, partner warp holds the other half.
+        float s1 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s1 += __uint_as_float(v[j]) + __ldg(p.bias + n_base + c + j);
+        }
+        red1[half * 128 + row_in_tile] = s1;
+        named_bar_sync(1 + q, 64);
+        const float mean = (red1[row_in_tile] + red1[128 + row_in_tile]) * (1.0f / BN);
+        float s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]) + __ldg(p.bias + n_base + c + j) - mean;
+            s2 += x * x;
+          }
+        }
+        red2[half * 128 + row_in_tile] = s2;
+        named_bar_sync(1 + q, 64);
+        const float var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
+        const float rstd = rsqrtf(var + 1e-5f);
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n_base;
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const int n = n_base + c + j;
+            float x0 = (__uint_as_float(v[j]) + __ldg(p.bias + n) - mean) * rstd;
+            float x1 = (__uint_as_float(v[j + 1]) + __ldg(p.bias + n + 1) - mean) * rstd;
+            x0 = gelu_erf(x0 * __ldg(p.ln_gamma + n) + __ldg(p.ln_beta + n));
+            x1 = gelu_erf(x1 * __ldg(p.ln_gamma + n + 1) + __ldg(p.ln_beta + n + 1));
+            o[j >> 1] = pack_bf16x2(x0, x1);
+          }
+          if (row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(orow + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+        }
+      } else if constexpr (EPI == EPI_ARGMAX) {
+        float best = -INFINITY;
+        int best_i = 0x7fffffff;
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+          const int n0 = n_base + c;
+          if (n0 < p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + j;
+              if (n < p.N) {
+                const float x = __uint_as_float(v[j]) + __ldg(bias_g + n);
+                if (x > best) {  // strict: lowest index wins among equals (torch.argmax)
+                  best = x;
+                  best_i = n;
+                }
+              }
+            }
+          }
+        }
+        if (row_ok && best_i != 0x7fffffff) atomicMax(p.argmax + out_row, argmax_pack(best, best_i));
+      } else {
+        bool zero_row = false;
+        if constexpr (EPI == EPI_F32) {
+          if (p.n_valid != nullptr && row_ok) {
+            const int seq = int(out_row / p.frames_per_seq);
+            const int t = int(out_row - (long long)seq * p.frames_per_seq);
+            zero_row = t >= __ldg(p.n_valid + seq);
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+          const int n0 = n_base + c;
+          if (row_ok && n0 < p.N) {
+            const bool full_chunk = (n0 + 32 <= p.N);
+            if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
+              __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + gcol + n0;
+              if (full_chunk) {
+                uint32_t o[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float x0 = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
+                  float x1 = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + n0 + j + 1) : 0.f);
+                  if constexpr (EPI == EPI_BF16_GELU) {
+                    x0 = gelu_erf(x0);
+                    x1 = gelu_erf(x1);
+                  }
+                  o[j >> 1] = pack_bf16x2(x0, x1);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              } else {
+                for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+                  float x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
+                  if constexpr (EPI == EPI_BF16_GELU) x = gelu_erf(x);
+                  orow[j] = __float2bfloat16(x);
+                }
+              }
+            } else {  // fp32 outputs
+              float* orow = reinterpret_cast<float*>(p.out) + out_row * p.ldo + gcol + n0;
+              const float* rrow = nullptr;
+              if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) rrow = p.resid + out_row * p.ldo + gcol + n0;
+              if (full_chunk) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  float4 x;
+                  x.x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
+                  x.y = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + n0 + j + 1) : 0.f);
+                  x.z = __uint_as_float(v[j + 2]) + (bias_g ? __ldg(bias_g + n0 + j + 2) : 0.f);
+                  x.w = __uint_as_float(v[j + 3]) + (bias_g ? __ldg(bias_g + n0 + j + 3) : 0.f);
+                  if constexpr (EPI == EPI_F32_GELU_RESID) {
+                    x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                  }
+                  if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) {
+                    const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
+                    x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                  }
+                  if (zero_row) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                  *reinterpret_cast<float4*>(orow + j) = x;
+                }
+              } else {
+                for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
+                  float x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
+                  if constexpr (EPI == EPI_F32_GELU_RESID) x = gelu_erf(x);
+                  if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) x += rrow[j];
+                  if (zero_row) x = 0.f;
+                  orow[j] = x;
+                }
+              }
+            }
+          }
+        }
+      }
+
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (C::ACC_STAGES == 2) {
+        as ^= 1;
+        if (as == 0) aph ^= 1;
+      } else {
+        aph ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TmapKey {
+  const void* base;
+  int rank;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  bool operator<(const TmapKey& o) const {
+    if (base != o.base) return base < o.base;
+    if (rank != o.rank) return rank < o.rank;
+    for (int i = 0; i < 5; ++i) if (dims[i] != o.dims[i]) return dims[i] < o.dims[i];
+    for (int i = 0; i < 4; ++i) if (strides[i] != o.strides[i]) return strides[i] < o.strides[i];
+    for (int i = 0; i < 5; ++i) if (box[i] != o.box[i]) return box[i] < o.box[i];
+    return false;
+  }
+};
+std::map<TmapKey, CUtensorMap> g_tmap_cache;
+std::mutex g_tmap_mu;
+
+int cached_tmap(CUtensorMap* out, const TmapKey& key) {
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) {
+    *out = it->second;
+    return OASR_OK;
+  }
+  OASR_TRY(make_tmap_bf16(out, key.base, key.rank, key.dims, key.strides, key.box, CU_TENSOR_MAP_SWIZZLE_128B));
+  if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
+  g_tmap_cache[key] = *out;
+  return OASR_OK;
+}
+
+inline uint64_t nz(long long v, uint64_t fallback) { return v > 0 ? (uint64_t)v : fallback; }
+
+template <int BN, int EPI>
+int launch(const GemmArgs& a, cudaStream_t stream) {
+  using C = GemmCfg<BN>;
+  const int k_pad = a.k_pad > 0 ? a.k_pad : ((a.a_inner + BK - 1) / BK) * BK;
+  GemmKernelParams p;
+  p.rows_per_batch = a.rows_per_batch;
+  p.batches = a.batches;
+  p.groups = a.groups;
+  p.N = a.N;
+  p.m_tiles_per_batch = (a.rows_per_batch + BM - 1) / BM;
+  p.n_tiles = (a.N + BN - 1) / BN;
+  p.total_tiles = p.m_tiles_per_batch * a.batches * a.groups * p.n_tiles;
+  p.kb_per_tap = k_pad / BK;
+  p.k_blocks = p.kb_per_tap * a.taps;
+  p.P = a.P;
+  const int n_cap = a.N < BN ? ((a.N + 15) / 16) * 16 : BN;   // columns one tile really computes
+  p.umma_n = n_cap > 256 ? 256 : n_cap;
+  p.b_box_rows = p.umma_n;
+  p.stage_tx_bytes = C::A_BYTES + (uint32_t)((n_cap + p.b_box_rows - 1) / p.b_box_rows) * p.b_box_rows * BK * 2;
+  p.ldo = a.ldo;
+  p.out_batch_rows = a.out_batch_rows > 0 ? a.out_batch_rows : a.rows_per_batch;
+  p.out = a.out;
+  p.bias = a.bias;
+  p.resid = a.resid;
+  p.ln_gamma = a.ln_gamma;
+  p.ln_beta = a.ln_beta;
+  p.argmax = a.argmax;
+  p.n_valid = a.n_valid;
+  p.frames_per_seq = a.frames_per_seq;
+  if (p.total_tiles == 0) return OASR_OK;
+
+  // A: {a_inner, P, U, batches, groups}; a unit-extent dimension still needs a legal (16-byte multiple) stride
+  TmapKey ka{};
+  ka.base = a.A;
+  ka.rank = 5;
+  const uint64_t pos_stride_b = (uint64_t)a.a_pos_stride * 2;
+  ka.dims[0] = (uint64_t)a.a_inner; ka.dims[1] = (uint64_t)a.P; ka.dims[2] = (uint64_t)a.a_positions;
+  ka.dims[3] = (uint64_t)a.batches; ka.dims[4] = (uint64_t)a.groups;
+  ka.strides[0] = nz(a.a_p_stride * 2, pos_stride_b);
+  ka.strides[1] = pos_stride_b;
+  ka.strides[2] = nz(a.a_batch_stride * 2, pos_stride_b * (uint64_t)a.a_positions);
+  ka.strides[3] = nz(a.a_group_stride * 2, ka.strides[2] * (uint64_t)a.batches);
+  ka.box[0] = BK; ka.box[1] = 1; ka.box[2] = BM; ka.box[3] = 1; ka.box[4] = 1;
+  // W: {taps*k_pad, N, groups}
+  TmapKey kw{};
+  kw.base = a.W;
+  kw.rank = 3;
+  const uint64_t wk = (uint64_t)a.taps * k_pad;
+  kw.dims[0] = wk; kw.dims[1] = (uint64_t)a.N; kw.dims[2] = (uint64_t)a.groups;
+  kw.strides[0] = wk * 2;
+  kw.strides[1] = wk * 2 * (uint64_t)a.N;
+  kw.box[0] = BK; kw.box[1] = (uint32_t)p.b_box_rows; kw.box[2] = 1;
+  CUtensorMap tmA, tmB;
+  OASR_TRY(cached_tmap(&tmA, ka));
+  OASR_TRY(cached_tmap(&tmB, kw));
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    OASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int grid = p.total_tiles < device_sm_count() ? p.total_tiles : device_sm_count();
+  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+}  // namespace
+
+int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
+  OASR_REQUIRE(a.A && a.W && a.rows_per_batch >= 0 && a.batches >= 1 && a.groups >= 1 && a.N > 0 && a.a_inner > 0 &&
+                   a.taps >= 1 && a.P >= 1 && a.a_positions > 0,
+               "gemm: bad arguments");
+  OASR_REQUIRE(a.a_inner % 8 == 0, "gemm: inner extent must be a multiple of 8 (16-byte TMA rows)");
+  OASR_REQUIRE(a.k_pad % 64 == 0, "gemm: k_pad must be a multiple of 64");
+  OASR_REQUIRE(a.a_pos_stride % 8 == 0 && a.a_p_stride % 8 == 0 && a.a_batch_stride % 8 == 0 &&
+                   a.a_group_stride % 8 == 0 && a.a_pos_stride > 0,
+               "gemm: A strides must be multiples of 8 elements");
+  OASR_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+               "gemm: operands must be 16-byte aligned");
+  OASR_REQUIRE(a.N % 8 == 0 || a.epilogue == EPI_ARGMAX, "gemm: N must be a multiple of 8");
+  if (a.epilogue != EPI_ARGMAX) {
+    OASR_REQUIRE(a.out != nullptr && a.ldo >= a.N * a.groups, "gemm: output missing");
+    OASR_REQUIRE(a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
+                 "gemm: output rows must be 16-byte aligned");
+  }
+  switch (a.epilogue) {
+    case EPI_BF16: return launch<256, EPI_BF16>(a, stream);
+    case EPI_BF16_GELU: return launch<256, EPI_BF16_GELU>(a, stream);
+    case EPI_F32: return launch<256, EPI_F32>(a, stream);
+    case EPI_F32_RESID:
+      OASR_REQUIRE(a.resid != nullptr, "gemm: residual missing");
+      return launch<256, EPI_F32_RESID>(a, stream);
+    case EPI_F32_GELU_RESID:
+      OASR_REQUIRE(a.resid != nullptr && a.N <= 128, "gemm: gelu+residual epilogue needs a residual and N <= 128");
+      return launch<128, EPI_F32_GELU_RESID>(a, stream);
+    case EPI_ARGMAX:
+      OASR_REQUIRE(a.argmax != nullptr && a.bias != nullptr && a.groups == 1, "gemm: argmax buffer / bias missing");
+      return launch<256, EPI_ARGMAX>(a, stream);
+    case EPI_LN_GELU_BF16:
+      OASR_REQUIRE(a.N == 512 && a.groups == 1 && a.bias && a.ln_gamma && a.ln_beta,
+                   "gemm: LN epilogue needs N == 512 and bias/gamma/beta");
+      return launch<512, EPI_LN_GELU_BF16>(a, stream);
+    default: return fail(OASR_ERR_INVALID, "gemm: unknown epilogue");
+  }
+}
+
+}  // namespace oasr

@@ -1,0 +1,312 @@
+// HBM-bound front of the path: waveform normalisation (a8), FE layer 0 (a9), row LayerNorm (a12/a14),
+// and the zero-padded bf16 copy that feeds the positional conv (a13).
+#include "host_util.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace oasr {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8 wave normalisation: pass 1 = per-slice (sum, sum of squares) in fp64, pass 2 = normalise.
+// grid (WAVE_NORM_SLICES, B), 256 threads.
+// ---------------------------------------------------------------------------------------------
+__global__ void wave_stats_kernel(const float* __restrict__ in, const int* __restrict__ n_samples, int L,
+                                  long long in_stride, double* __restrict__ partials) {
+  const int b = blockIdx.y, slice = blockIdx.x;
+  const int n = min(n_samples[b], L);
+  const int per = (n + WAVE_NORM_SLICES - 1) / WAVE_NORM_SLICES;
+  const int lo = slice * per, hi = min(n, lo + per);
+  const float* x = in + (long long)b * in_stride;
+  double s = 0.0, ss = 0.0;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const double v = (double)__ldg(x + i);
+    s += v;
+    ss += v * v;
+  }
+  __shared__ double sh[2][8];
+  s = warp_sum_d(s);
+  ss = warp_sum_d(ss);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sh[0][w] = s;
+    sh[1][w] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      a += sh[0][i];
+      c += sh[1][i];
+    }
+    partials[((long long)b * WAVE_NORM_SLICES + slice) * 2 + 0] = a;
+    partials[((long long)b * WAVE_NORM_SLICES + slice) * 2 + 1] = c;
+  }
+}
+
+__global__ void wave_apply_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                  const int* __restrict__ n_samples, int L, long long in_stride, long long out_stride,
+                                  const double* __restrict__ partials) {
+  const int b = blockIdx.y, slice = blockIdx.x;
+  const int n = min(n_samples[b], L);
+  __shared__ float sh_mean, sh_rstd;
+  if (threadIdx.x == 0) {
+    double s = 0, ss = 0;
+    for (int i = 0; i < WAVE_NORM_SLICES; ++i) {
+      s += partials[((long long)b * WAVE_NORM_SLICES + i) * 2 + 0];
+      ss += partials[((long long)b * WAVE_NORM_SLICES + i) * 2 + 1];
+    }
+    const double mean = n > 0 ? s / n : 0.0;
+    double var = n > 0 ? ss / n - mean * mean : 0.0;
+    if (var < 0) var = 0;
+    sh_mean = (float)mean;
+    sh_rstd = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const float mean = sh_mean, rstd = sh_rstd;
+  const int per = (L + WAVE_NORM_SLICES - 1) / WAVE_NORM_SLICES;
+  const int lo = slice * per, hi = min(L, lo + per);
+  const float* x = in + (long long)b * in_stride;
+  float* y = out + (long long)b * out_stride;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = i < n ? (__ldg(x + i) - mean) * rstd : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9 FE layer 0.  One warp per output frame pair; lane owns channels {2*lane + 64*j, +1 : j < 8}.
+// Weights [10][512] live in shared memory; stores are 128-byte coalesced bf16x2 rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int L0_K = 10, L0_S = 5, L0_C = 512;
+constexpr int L0_WARPS = 8;
+constexpr int L0_FRAMES_PER_WARP_ITER = 2;
+
+__global__ void __launch_bounds__(L0_WARPS * 32)
+fe_layer0_kernel(const float* __restrict__ wave, long long in_stride, int T0, const float* __restrict__ w,
+                 const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ out, long long out_batch_stride, int frames_per_block) {
+  __shared__ float2 sw[L0_K][L0_C / 2];
+  for (int i = threadIdx.x; i < L0_K * L0_C / 2; i += blockDim.x)
+    sw[i / (L0_C / 2)][i % (L0_C / 2)] = reinterpret_cast<const float2*>(w)[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const float* x = wave + (long long)b * in_stride;
+  __nv_bfloat16* o = out + (long long)b * out_batch_stride;
+
+  float2 bi[8], ga[8], be[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c2 = lane + 32 * j;  // float2 index: channels 2*c2, 2*c2+1
+    bi[j] = __ldg(reinterpret_cast<const float2*>(bias) + c2);
+    ga[j] = __ldg(reinterpret_cast<const float2*>(gamma) + c2);
+    be[j] = __ldg(reinterpret_cast<const float2*>(beta) + c2);
+  }
+
+  const int t_begin = blockIdx.x * frames_per_block;
+  const int t_end = min(T0, t_begin + frames_per_block);
+  for (int t = t_begin + warp * L0_FRAMES_PER_WARP_ITER; t < t_end; t += L0_WARPS * L0_FRAMES_PER_WARP_ITER) {
+    const bool two = (t + 1 < t_end);
+    float xs[L0_K + L0_S];
+#pragma unroll
+    for (int k = 0; k < L0_K + L0_S; ++k) xs[k] = (k < L0_K || two) ? __ldg(x + (long long)t * L0_S + k) : 0.f;
+
+    float2 a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j] = bi[j];
+      a1[j] = bi[j];
+    }
+#pragma unroll
+    for (int k = 0; k < L0_K; ++k) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 wv = sw[k][lane + 32 * j];
+        a0[j].x = fmaf(wv.x, xs[k], a0[j].x);
+        a0[j].y = fmaf(wv.y, xs[k], a0[j].y);
+        a1[j].x = fmaf(wv.x, xs[k + L0_S], a1[j].x);
+        a1[j].y = fmaf(wv.y, xs[k + L0_S], a1[j].y);
+      }
+    }
+    // LayerNorm over 512 channels (two-pass, fp32) for both frames
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s0 += a0[j].x + a0[j].y;
+      s1 += a1[j].x + a1[j].y;
+    }
+    const float m0 = warp_sum(s0) * (1.0f / L0_C), m1 = warp_sum(s1) * (1.0f / L0_C);
+    float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[j].x -= m0; a0[j].y -= m0; a1[j].x -= m1; a1[j].y -= m1;
+      v0 += a0[j].x * a0[j].x + a0[j].y * a0[j].y;
+      v1 += a1[j].x * a1[j].x + a1[j].y * a1[j].y;
+    }
+    const float r0 = rsqrtf(warp_sum(v0) * (1.0f / L0_C) + 1e-5f);
+    const float r1 = rsqrtf(warp_sum(v1) * (1.0f / L0_C) + 1e-5f);
+    uint32_t* o0 = reinterpret_cast<uint32_t*>(o + (long long)t * L0_C);
+    uint32_t* o1 = reinterpret_cast<uint32_t*>(o + (long long)(t + 1) * L0_C);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y0 = gelu_erf(a0[j].x * r0 * ga[j].x + be[j].x);
+      const float y1 = gelu_erf(a0[j].y * r0 * ga[j].y + be[j].y);
+      o0[lane + 32 * j] = pack_bf16x2(y0, y1);
+      if (two) {
+        const float z0 = gelu_erf(a1[j].x * r1 * ga[j].x + be[j].x);
+        const float z1 = gelu_erf(a1[j].y * r1 * ga[j].y + be[j].y);
+        o1[lane + 32 * j] = pack_bf16x2(z0, z1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row LayerNorm: one warp per row, D = 64 * VEC2 * ... kept in registers.  D % 64 == 0, D <= 2048.
+// ---------------------------------------------------------------------------------------------
+template <bool IN_BF16>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int batches, int rows_per_batch, int D,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
+                 float* __restrict__ out_f32) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  const long long total = (long long)batches * rows_per_batch;
+  if (row >= total) return;
+  const int b = int(row / rows_per_batch);
+  const int t = int(row - (long long)b * rows_per_batch);
+  const int npairs = D >> 6;  // float2 per lane
+  float2 v[32];
+  float s = 0.f;
+  if (IN_BF16) {
+    const __nv_bfloat162* p =
+        reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(in) + (long long)b * in_batch_stride +
+                                                (long long)t * D);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < npairs) {
+        v[j] = __bfloat1622float2(p[lane + 32 * j]);
+        s += v[j].x + v[j].y;
+      }
+  } else {
+    const float2* p = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + (long long)b * in_batch_stride +
+                                                      (long long)t * D);
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < npairs) {
+        v[j] = p[lane + 32 * j];
+        s += v[j].x + v[j].y;
+      }
+  }
+  const float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < npairs) {
+      v[j].x -= mean;
+      v[j].y -= mean;
+      q += v[j].x * v[j].x + v[j].y * v[j].y;
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+  const float2* g2 = reinterpret_cast<const float2*>(gamma);
+  const float2* b2 = reinterpret_cast<const float2*>(beta);
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (j < npairs) {
+      const float2 g = __ldg(g2 + lane + 32 * j), bb = __ldg(b2 + lane + 32 * j);
+      const float y0 = v[j].x * rstd * g.x + bb.x;
+      const float y1 = v[j].y * rstd * g.y + bb.y;
+      if (out_bf16) reinterpret_cast<uint32_t*>(out_bf16 + row * D)[lane + 32 * j] = pack_bf16x2(y0, y1);
+      if (out_f32) reinterpret_cast<float2*>(out_f32 + row * D)[lane + 32 * j] = make_float2(y0, y1);
+    }
+}
+
+__global__ void pad_cast_kernel(const float* __restrict__ x, int T, int d, int pad, __nv_bfloat16* __restrict__ out,
+                                long long total_vec4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index of a 4-element group
+  if (i >= total_vec4) return;
+  const int d4 = d >> 2;
+  const long long row = i / d4;
+  const int c4 = int(i - row * d4);
+  const int b = int(row / T);
+  const int t = int(row - (long long)b * T);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+  uint2 o;
+  o.x = pack_bf16x2(v.x, v.y);
+  o.y = pack_bf16x2(v.z, v.w);
+  const long long orow = (long long)b * (T + 2 * pad) + pad + t;
+  reinterpret_cast<uint2*>(out + orow * d)[c4] = o;
+}
+
+}  // namespace
+
+int wave_norm(const float* in, float* out, const int* n_samples, int B, int L, long long in_stride,
+              long long out_stride, double* partials, cudaStream_t stream) {
+  OASR_REQUIRE(in && out && n_samples && partials && B > 0 && L > 0, "wave_norm: bad arguments");
+  dim3 grid(WAVE_NORM_SLICES, B);
+  wave_stats_kernel<<<grid, 256, 0, stream>>>(in, n_samples, L, in_stride, partials);
+  wave_apply_kernel<<<grid, 256, 0, stream>>>(in, out, n_samples, L, in_stride, out_stride, partials);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+int fe_layer0(const float* wave, long long in_stride, int B, int L, const float* w, const float* bias,
+              const float* gamma, const float* beta, void* out_bf16, long long out_batch_stride_elems, int T0,
+              cudaStream_t stream) {
+  OASR_REQUIRE(wave && w && bias && gamma && beta && out_bf16 && B > 0, "fe_layer0: bad arguments");
+  OASR_REQUIRE(T0 == (L >= L0_K ? (L - L0_K) / L0_S + 1 : 0), "fe_layer0: T0 does not match L");
+  if (T0 == 0) return OASR_OK;
+  // ~4 blocks per SM per batch row keeps the tail short without re-reading the 20 KB of weights too often
+  int blocks_x = (device_sm_count() * 8 + B - 1) / B;
+  if (blocks_x < 1) blocks_x = 1;
+  int frames_per_block = (T0 + blocks_x - 1) / blocks_x;
+  const int gran = L0_WARPS * L0_FRAMES_PER_WARP_ITER;
+  frames_per_block = ((frames_per_block + gran - 1) / gran) * gran;
+  blocks_x = (T0 + frames_per_block - 1) / frames_per_block;
+  dim3 grid(blocks_x, B);
+  fe_layer0_kernel<<<grid, L0_WARPS * 32, 0, stream>>>(wave, in_stride, T0, w, bias, gamma, beta,
+                                                        reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                        out_batch_stride_elems, frames_per_block);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
+                   const float* gamma, const float* beta, void* out_bf16, float* out_f32, cudaStream_t stream) {
+  OASR_REQUIRE(in && gamma && beta && (out_bf16 || out_f32), "layernorm: bad arguments");
+  OASR_REQUIRE(D % 64 == 0 && D <= 2048 && D > 0, "layernorm: D must be a multiple of 64 and <= 2048");
+  const long long total = (long long)batches * rows_per_batch;
+  if (total == 0) return OASR_OK;
+  const int rows_per_block = 8;
+  const unsigned grid = (unsigned)((total + rows_per_block - 1) / rows_per_block);
+  if (in_is_bf16)
+    layernorm_kernel<true><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,
+                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  else
+    layernorm_kernel<false><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,
+                                                      reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+int pad_cast_bf16(const float* x, int B, int T, int d, int pad, void* out_bf16, cudaStream_t stream) {
+  OASR_REQUIRE(x && out_bf16 && d % 4 == 0, "pad_cast: bad arguments");
+  const long long total = (long long)B * T * (d / 4);
+  if (total == 0) return OASR_OK;
+  pad_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, T, d, pad,
+                                                                       reinterpret_cast<__nv_bfloat16*>(out_bf16), total);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+}  // namespace oasr

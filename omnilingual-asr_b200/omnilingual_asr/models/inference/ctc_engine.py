@@ -1,0 +1,206 @@
+"""Python owner of one liboasr engine handle (one per GPU).
+
+This is the slot the reference fills with an HTTPS call (gemini_pipeline.py:512-530): a batch of
+fixed-length windows goes in, token ids and their frame positions come out.  PyTorch is used only for
+device memory, streams and pinned buffers; every arithmetic step runs inside liboasr's sm_100a kernels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+from typing import List, Mapping, Optional, Sequence
+
+import numpy as np
+import torch
+
+from omnilingual_asr import _native as N
+from omnilingual_asr.models.config import CtcModelConfig, get_model_config
+
+
+@dataclass
+class CtcBatchResult:
+    """Greedy CTC output of one batch of windows."""
+    token_ids: List[np.ndarray]      # per window: collapsed ids (int32)
+    token_frames: List[np.ndarray]   # per window: first frame index of each id
+    n_frames: List[int]              # valid frames per window
+    frame_ids: Optional[np.ndarray] = None   # [B, Tmax] per-frame arg-max (padded frames = blank)
+    hidden: Optional[torch.Tensor] = None    # [B, Tmax, d] final-LayerNorm output (fp32, device)
+
+
+def _as_config_struct(cfg: CtcModelConfig) -> N.OasrConfig:
+    c = N.OasrConfig()
+    c.d_model, c.n_layers, c.n_heads, c.d_ffn = cfg.d_model, cfg.n_layers, cfg.n_heads, cfg.d_ffn
+    c.vocab, c.fe_dim, c.pos_kernel, c.pos_groups = cfg.vocab, cfg.fe_dim, cfg.pos_kernel, cfg.pos_groups
+    if len(cfg.fe_layers) > 8:
+        raise ValueError("at most 8 feature-extractor layers")
+    c.n_fe_layers = len(cfg.fe_layers)
+    for i, (ch, k, s) in enumerate(cfg.fe_layers):
+        if ch != cfg.fe_dim:
+            raise ValueError("all feature-extractor layers must have fe_dim channels")
+        c.fe_kernel[i], c.fe_stride[i] = k, s
+    c.blank_id = cfg.blank_id
+    return c
+
+
+class CtcEngine:
+    """One CUDA engine: weights resident in HBM, forward = a8..a16 on the calling thread's stream."""
+
+    def __init__(self, model: str | CtcModelConfig, device: Optional[torch.device | str | int] = None):
+        self.cfg = get_model_config(model)
+        self._lib = N.load()  # raises when liboasr.so is missing: no CPU fallback
+        if not torch.cuda.is_available():
+            raise RuntimeError("omniASR CTC engine needs a CUDA device (B200, sm_100a); none is visible")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("CtcEngine device must be a CUDA device")
+        self._cstruct = _as_config_struct(self.cfg)
+        self._handle = C.c_void_p(0)
+        self._lock = threading.Lock()
+        self._finalized = False
+        with torch.cuda.device(self.device):
+            N.check(self._lib.oasr_create(C.byref(self._cstruct), C.byref(self._handle)), "oasr_create")
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, weights: Mapping[str, torch.Tensor | np.ndarray], finalize: bool = True) -> None:
+        """Copy every tensor named in cfg.weight_shapes() into the engine (host or device sources)."""
+        shapes = self.cfg.weight_shapes()
+        missing = [k for k in shapes if k not in weights]
+        if missing:
+            raise ValueError(f"missing weights: {missing[:5]}{'...' if len(missing) > 5 else ''}")
+        with self._lock, torch.cuda.device(self.device):
+            for name, shape in shapes.items():
+                t = weights[name]
+                if isinstance(t, np.ndarray):
+                    t = torch.from_numpy(t)
+                if tuple(t.shape) != tuple(shape):
+                    raise ValueError(f"{name}: expected shape {shape}, got {tuple(t.shape)}")
+                if t.dtype == torch.bfloat16:
+                    dt = N.DTYPE_BF16
+                else:
+                    t = t.to(torch.float32)
+                    dt = N.DTYPE_F32
+                t = t.contiguous()
+                shp = (C.c_int64 * len(shape))(*shape)
+                N.check(self._lib.oasr_load_weight(self._handle, name.encode(), N.ptr(t), dt, shp, len(shape)),
+                        f"oasr_load_weight({name})")
+            if finalize:
+                N.check(self._lib.oasr_finalize_weights(self._handle), "oasr_finalize_weights")
+                self._finalized = True
+
+    def finalize(self) -> None:
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_finalize_weights(self._handle), "oasr_finalize_weights")
+            self._finalized = True
+
+    # ------------------------------------------------------------------ forward
+    def feature_length(self, n_samples: int) -> int:
+        return int(self._lib.oasr_feature_length(C.byref(self._cstruct), int(n_samples)))
+
+    def forward(self, wave: torch.Tensor, n_samples: Sequence[int], *, normalised: bool = False,
+                return_hidden: bool = False, return_frame_ids: bool = True) -> CtcBatchResult:
+        """wave: [B, L] fp32 on this engine's device, zero padded past n_samples[b]."""
+        if wave.dim() != 2 or wave.dtype != torch.float32 or wave.device != self.device:
+            raise ValueError("wave must be a [B, L] float32 tensor on the engine's device")
+        B, L = wave.shape
+        if len(n_samples) != B:
+            raise ValueError("n_samples must have one entry per window")
+        if wave.stride(1) != 1:
+            wave = wave.contiguous()
+        T = self.feature_length(L)
+        ns = (C.c_int32 * B)(*[int(v) for v in n_samples])
+        with self._lock, torch.cuda.device(self.device):
+            frame_ids = torch.empty((B, max(T, 1)), dtype=torch.int32, device=self.device)
+            out_ids = torch.empty_like(frame_ids)
+            out_frames = torch.empty_like(frame_ids)
+            out_lens = torch.zeros((B,), dtype=torch.int32, device=self.device)
+            hidden = (torch.empty((B, T, self.cfg.d_model), dtype=torch.float32, device=self.device)
+                      if return_hidden else None)
+            flags = N.FLAG_INPUT_NORMALISED if normalised else 0
+            N.check(self._lib.oasr_forward_ctc(
+                self._handle, N.ptr(wave), wave.stride(0), C.cast(ns, C.c_void_p), B, L, flags,
+                N.ptr(frame_ids), N.ptr(hidden), N.ptr(out_ids), N.ptr(out_frames), N.ptr(out_lens),
+                N.stream_ptr()), "oasr_forward_ctc")
+            lens = out_lens.cpu().numpy()          # synchronises the stream
+            ids_h = out_ids.cpu().numpy()
+            frames_h = out_frames.cpu().numpy()
+            fids = frame_ids[:, :T].cpu().numpy() if return_frame_ids else None
+        return CtcBatchResult(
+            token_ids=[ids_h[b, :lens[b]].copy() for b in range(B)],
+            token_frames=[frames_h[b, :lens[b]].copy() for b in range(B)],
+            n_frames=[self.cfg.feature_length(int(v)) for v in n_samples],
+            frame_ids=fids, hidden=hidden)
+
+    def transcribe_host(self, wave: np.ndarray | torch.Tensor, n_samples: Sequence[int], *,
+                        normalised: bool = False, return_frame_ids: bool = False) -> CtcBatchResult:
+        """Same from host memory through oasr_transcribe_host (H2D + forward + D2H inside the call)."""
+        if isinstance(wave, torch.Tensor):
+            if wave.device.type != "cpu" or wave.dtype != torch.float32 or wave.dim() != 2 or wave.stride(1) != 1:
+                raise ValueError("wave must be a [B, L] float32 CPU tensor with unit inner stride")
+            B, L = wave.shape
+            stride = wave.stride(0)
+        else:
+            wave = np.ascontiguousarray(wave, dtype=np.float32)
+            if wave.ndim != 2:
+                raise ValueError("wave must be [B, L]")
+            B, L = wave.shape
+            stride = L
+        T = self.feature_length(L)
+        ns = (C.c_int32 * B)(*[int(v) for v in n_samples])
+        out_ids = np.empty((B, max(T, 1)), dtype=np.int32)
+        out_frames = np.empty_like(out_ids)
+        out_lens = np.zeros((B,), dtype=np.int32)
+        fids = np.empty_like(out_ids) if return_frame_ids else None
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_transcribe_host(
+                self._handle, N.ptr(wave), stride, C.cast(ns, C.c_void_p), B, L,
+                N.FLAG_INPUT_NORMALISED if normalised else 0, N.ptr(out_ids), N.ptr(out_frames), N.ptr(out_lens),
+                N.ptr(fids), N.stream_ptr()), "oasr_transcribe_host")
+        return CtcBatchResult(
+            token_ids=[out_ids[b, :out_lens[b]].copy() for b in range(B)],
+            token_frames=[out_frames[b, :out_lens[b]].copy() for b in range(B)],
+            n_frames=[self.cfg.feature_length(int(v)) for v in n_samples],
+            frame_ids=fids[:, :T] if fids is not None else None)
+
+    # ------------------------------------------------------------------ debug / accounting
+    def debug_forward(self, wave: torch.Tensor, n_samples: Sequence[int], stop_stage: int, *,
+                      normalised: bool = False) -> None:
+        B, L = wave.shape
+        ns = (C.c_int32 * B)(*[int(v) for v in n_samples])
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_debug_forward(
+                self._handle, N.ptr(wave), wave.stride(0), C.cast(ns, C.c_void_p), B, L,
+                N.FLAG_INPUT_NORMALISED if normalised else 0, stop_stage, N.stream_ptr()), "oasr_debug_forward")
+            torch.cuda.synchronize(self.device)
+
+    def debug_buffer(self, name: str) -> torch.Tensor:
+        """Copy of an internal device buffer (see oasr_debug_buffer) as a torch tensor."""
+        p = C.c_void_p(0)
+        shape = (C.c_int64 * 4)()
+        dt = C.c_int32(0)
+        N.check(self._lib.oasr_debug_buffer(self._handle, name.encode(), C.byref(p), shape, C.byref(dt)),
+                "oasr_debug_buffer")
+        dims = [int(v) for v in shape if v > 0]
+        dtype = torch.bfloat16 if dt.value == N.DTYPE_BF16 else torch.float32
+        out = torch.empty(dims, dtype=dtype, device=self.device)
+        nbytes = out.numel() * out.element_size()
+        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, nbytes, 3)  # 3 = DeviceToDevice
+        if int(rc) != 0:
+            raise RuntimeError(f"cudaMemcpy of debug buffer {name} failed: {rc}")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.oasr_launch_count(self._handle))
+
+    def close(self) -> None:
+        if getattr(self, "_handle", None) and self._handle.value:
+            with torch.cuda.device(self.device):
+                self._lib.oasr_destroy(self._handle)
+            self._handle = C.c_void_p(0)
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
