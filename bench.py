@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds transcribed per second (inverse RTF) for omniASR CTC on B200.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our arm, one JSON line on stdout
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                       # the CPU oracle timed on the host cores
+
+A step is one pass of the hot path (a8..a16: normalise -> conv FE -> pos-conv -> encoder -> CTC arg-max ->
+collapse) over one batch of `--batch` synthetic 30 s windows per GPU (BASELINE.json configs[1]:
+omniASR_CTC_1B, 32 x 30 s, bf16 operands / fp32 accumulate, random-init weights).
+  value  windows resident in HBM when the timed region starts (device time, CUDA events, max over ranks)
+  e2e    the same through oasr_transcribe_host from pinned HOST buffers (H2D + forward + D2H every step)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT), str(ROOT / "omnilingual-asr_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WINDOW_SEC = 30.0
+SR = 16000
+METRIC = "audio-sec/sec (inverse RTF)"
+UNIT = "audio-s/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="omniASR_CTC_1B")
+    ap.add_argument("--batch", type=int, default=32, help="30 s windows per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-windows", type=int, default=2, help="windows in the bounded CPU sample")
+    return ap.parse_args()
+
+
+def synthetic_windows(batch: int, seed: int) -> torch.Tensor:
+    """[batch, 480000] fp32: unit Gaussian noise plus a few tones (non-degenerate LayerNorm statistics)."""
+    g = torch.Generator().manual_seed(seed)
+    L = int(WINDOW_SEC * SR)
+    x = torch.randn(batch, L, generator=g)
+    t = torch.arange(L, dtype=torch.float32) / SR
+    for f, a in ((220.0, 0.5), (1333.0, 0.25), (3100.0, 0.1)):
+        x += a * torch.sin(2 * np.pi * f * t)[None]
+    return x
+
+
+def flops_per_window(cfg, T: int) -> dict:
+    """Algorithmic FLOPs (2 * MAC) of each stage for one 30 s window."""
+    d, F, Lyr, V = cfg.d_model, cfg.d_ffn, cfg.n_layers, cfg.vocab
+    n = int(WINDOW_SEC * SR)
+    lens = []
+    for _, k, s in cfg.fe_layers:
+        n = (n - k) // s + 1
+        lens.append(n)
+    fe = [2.0 * lens[0] * 512 * 10] + [2.0 * lens[i] * 512 * 512 * cfg.fe_layers[i][1] for i in range(1, len(lens))]
+    cg = d // cfg.pos_groups
+    return {
+        "fe_layer0": fe[0], "fe_conv_1_6": sum(fe[1:]), "feature_proj": 2.0 * T * 512 * d,
+        "posconv": 2.0 * T * d * cg * cfg.pos_kernel,
+        "qkv_gemm": Lyr * 2.0 * T * d * 3 * d, "outproj_gemm": Lyr * 2.0 * T * d * d,
+        "ffn1_gemm": Lyr * 2.0 * T * d * F, "ffn2_gemm": Lyr * 2.0 * T * d * F,
+        "attention": Lyr * 4.0 * T * T * d, "ctc_head_argmax": 2.0 * T * d * V,
+    }
+
+
+def measured_peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_throughput(model: str, windows: int, reps: int = 1, warmup: int = 0):
+    """Times the CPU oracle (PyTorch eager fp32, all host threads) on `windows` 30 s windows."""
+    from oracle import ctc_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.PRESETS[model]
+    w = O.init_weights(cfg, seed=0)
+    wave = synthetic_windows(windows, 1234)
+    ns = [wave.shape[1]] * windows
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + reps):
+            t0 = time.perf_counter()
+            wn = O.wave_layer_norm(wave, ns)
+            out = O.forward(w, wn, ns, cfg)
+            for b in range(windows):
+                O.greedy_collapse(out.frame_ids[b], out.n_frames[b])
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return windows * WINDOW_SEC / (sum(times) / len(times)), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    windows = 1
+    t_all0 = time.perf_counter()
+    val, cores, times = cpu_oracle_throughput(args.model, windows, reps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model}, 32 x 30 s synthetic 16 kHz windows (BASELINE configs[1])",
+                   "sample": f"{windows} x 30 s window per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{windows} x 30 s window per step, {args.steps} steps, PyTorch eager fp32 oracle"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    from omnilingual_asr.models.config import get_model_config
+    from omnilingual_asr.models.inference.ctc_engine import CtcEngine
+    from omnilingual_asr.models.weights import random_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    cfg = get_model_config(args.model)
+    B, L = args.batch, int(WINDOW_SEC * SR)
+    T = cfg.feature_length(L)
+    eng = CtcEngine(cfg, device=dev)
+    eng.load_state_dict(random_weights(cfg, 0, dev))
+    host = synthetic_windows(B, 1234 + rank).pin_memory()
+    ns = [L] * B
+    wave_dev = host.to(dev)
+    audio_per_step = world * B * WINDOW_SEC
+
+    # ---------------------------------------------------------------- device-resident leg ("value")
+    for _ in range(args.warmup):
+        eng.forward(wave_dev, ns, return_frame_ids=False)
+    eng.profile_read()
+    eng.profile(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        eng.forward(wave_dev, ns, return_frame_ids=False)
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count - n0
+    stage_ms = eng.profile_read()
+    eng.profile(False)
+    clk = clocks.stop() if rank == 0 else {}
+    value = audio_per_step * args.steps / (dev_ms / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end leg (host buffers)
+    for _ in range(min(args.warmup, 2)):
+        eng.transcribe_host(host, ns)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = eng.transcribe_host(host, ns)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_val = audio_per_step * args.steps / e2e_s
+    h2d = B * L * 4
+    d2h = 2 * B * T * 4 + B * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks, peak_src = measured_peaks()
+    fl = flops_per_window(cfg, T)
+    stages = {}
+    total_stage_ms = sum(ms for ms, _ in stage_ms.values()) or 1.0
+    for name, (ms, cnt) in stage_ms.items():
+        if cnt == 0:
+            continue
+        entry = {"ms_per_step": ms / args.steps, "share": ms / total_stage_ms, "launch_groups": cnt}
+        if name in fl and ms > 0:
+            entry["tflops"] = fl[name] * B * args.steps / (ms / 1e3) / 1e12
+        stages[name] = entry
+    gemm_names = ["qkv_gemm", "outproj_gemm", "ffn1_gemm", "ffn2_gemm"]
+    g_ms = sum(stage_ms[n][0] for n in gemm_names)
+    g_cnt = sum(stage_ms[n][1] for n in gemm_names)
+    g_flops = sum(fl[n] for n in gemm_names) * B * args.steps
+    achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    roofline = {
+        "kernel": "gemm_kernel<256,*> (tcgen05 GEMM: encoder QKV / out-proj / FFN1 / FFN2)",
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+        "traffic": None,
+        "flops_per_launch": g_flops / max(g_cnt, 1), "avg_launch_ms": g_ms / max(g_cnt, 1),
+        "share_of_step": g_ms / total_stage_ms,
+        "whole_path_tflops": sum(fl.values()) * B * world * args.steps / (dev_ms / 1e3) / 1e12,
+        "stages": stages,
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.model}, {B} x 30 s synthetic 16 kHz windows per GPU (BASELINE configs[1]), "
+                               "random-init weights, bf16 operands / fp32 accumulate",
+                   "windows_per_gpu": B, "frames_per_window": T, "parallelism": f"dp{world} (window shards, no collective)",
+                   "l2": "inputs re-read from HBM every step: per-step working set (FE activations ~6 GB, encoder "
+                         "activations ~1.5 GB, weights 1.9 GB) is far larger than the 126 MB L2"},
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "oasr_transcribe_host (C-ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roofline,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        val, cores, times = cpu_oracle_throughput(args.model, args.cpu_windows, reps=1)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"{args.cpu_windows} x 30 s windows, one pass, PyTorch eager fp32 oracle "
+                                          f"({times[0]:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

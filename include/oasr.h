@@ -116,6 +116,17 @@ OASR_API int oasr_debug_buffer(OasrHandle h, const char* name, void** dev_ptr, i
 /* Kernel launches issued by this handle since creation (bench.py reports it as gpu_launches). */
 OASR_API int64_t oasr_launch_count(OasrHandle h);
 
+/* Per-stage device timing: when enabled, a CUDA event is recorded on the forward's stream at every stage
+ * boundary; oasr_profile_read synchronises, returns accumulated milliseconds and stage counts per category
+ * (arrays of OASR_PROF_NCAT entries) and resets the accumulators. */
+enum {
+  OASR_PROF_WAVE_NORM = 0, OASR_PROF_FE0, OASR_PROF_FE_CONV, OASR_PROF_LAYERNORM, OASR_PROF_PROJ,
+  OASR_PROF_POSCONV, OASR_PROF_QKV, OASR_PROF_ATTENTION, OASR_PROF_OUTPROJ, OASR_PROF_FFN1, OASR_PROF_FFN2,
+  OASR_PROF_CTC_HEAD, OASR_PROF_DECODE, OASR_PROF_END, OASR_PROF_NCAT
+};
+OASR_API int oasr_profile_enable(OasrHandle h, int32_t on);
+OASR_API int oasr_profile_read(OasrHandle h, double* ms, int64_t* counts, int32_t n);
+
 /* ---- per-stage entry points (unit parity; all pointers are device pointers) ------------------------- */
 OASR_API int oasr_wave_norm(const float* in, float* out, const int32_t* n_samples_dev, int32_t B, int32_t L, OasrStream stream);
 OASR_API int oasr_fe_layer0(const float* wave, int32_t B, int32_t L, const float* w_10x512, const float* bias,

@@ -137,6 +137,12 @@ struct OasrEngine {
   bool stage_used[STAGE_SLOTS] = {};
   int stage_next = 0;
   float* wave_raw = nullptr;        // [B, L] H2D landing buffer of oasr_transcribe_host
+  // optional per-stage timing (bench.py): an event at every stage boundary of the forward
+  bool profiling = false;
+  std::vector<std::pair<int, cudaEvent_t>> prof_marks;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[OASR_PROF_NCAT] = {};
+  int64_t prof_n[OASR_PROF_NCAT] = {};
   // shapes of the last forward (debug buffers)
   int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
   long long last_fe_pad = 0;
@@ -220,6 +226,19 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   e->ws_B = nB;
   e->ws_L = nL;
   return OASR_OK;
+}
+
+void prof_mark(OasrEngine* e, int cat, cudaStream_t st) {
+  if (!e->profiling) return;
+  cudaEvent_t ev;
+  if (!e->prof_pool.empty()) {
+    ev = e->prof_pool.back();
+    e->prof_pool.pop_back();
+  } else if (cudaEventCreate(&ev) != cudaSuccess) {
+    return;
+  }
+  cudaEventRecord(ev, st);
+  e->prof_marks.emplace_back(cat, ev);
 }
 
 // One FE conv layer (i >= 1) as an implicit GEMM with fused LayerNorm + GELU.
@@ -308,6 +327,7 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   e->stage_used[slot] = true;
 
   // a8
+  prof_mark(e, OASR_PROF_WAVE_NORM, st);
   const float* wv = wave_in;
   long long wv_stride = wave_stride;
   if (!(flags & OASR_FLAG_INPUT_NORMALISED)) {
@@ -317,6 +337,7 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
     wv_stride = L;
   }
   // a9
+  prof_mark(e, OASR_PROF_FE0, st);
   int t_prev = fe_len(c, L, 1);
   long long pad_prev = fe_pad_rows(t_prev);
   OASR_TRY(fe_layer0(wv, wv_stride, B, L, e->fe0_w, e->fe_bias[0], e->fe_g[0], e->fe_b[0], e->fe_buf[0],
@@ -324,6 +345,7 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   e->launches += 1;
   int cur = 0;
   // a10-a11
+  prof_mark(e, OASR_PROF_FE_CONV, st);
   for (int i = 1; i < c.n_fe_layers; ++i) {
     const int t_out = t_prev >= c.fe_kernel[i] ? (t_prev - c.fe_kernel[i]) / 2 + 1 : 0;
     const long long pad_out = fe_pad_rows(t_out);
@@ -336,10 +358,15 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   }
   e->last_fe_idx = cur;
   e->last_fe_pad = pad_prev;
-  if (stop_stage == 1 || T == 0) return OASR_OK;
+  if (stop_stage == 1 || T == 0) {
+    prof_mark(e, OASR_PROF_END, st);
+    return OASR_OK;
+  }
 
   // a12
+  prof_mark(e, OASR_PROF_LAYERNORM, st);
   OASR_TRY(layernorm_rows(e->fe_buf[cur], 1, pad_prev * 512, B, T, 512, e->proj_ln_g, e->proj_ln_b, e->lnbuf, nullptr, st));
+  prof_mark(e, OASR_PROF_PROJ, st);
   {
     GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, 512, 512, e->proj_w, d);
     a.bias = e->proj_bias;
@@ -351,18 +378,27 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
     OASR_TRY(gemm_bf16_tcgen05(a, st));
   }
   e->launches += 2;
-  if (stop_stage == 2) return OASR_OK;
+  if (stop_stage == 2) {
+    prof_mark(e, OASR_PROF_END, st);
+    return OASR_OK;
+  }
 
   // a13
+  prof_mark(e, OASR_PROF_POSCONV, st);
   OASR_TRY(run_posconv(e->x, B, T, d, c.pos_groups, c.pos_kernel, e->pos_kpad, e->pos_w, e->pos_bias, e->xpad, st));
   e->launches += 3;
-  if (stop_stage == 3) return OASR_OK;
+  if (stop_stage == 3) {
+    prof_mark(e, OASR_PROF_END, st);
+    return OASR_OK;
+  }
 
   // a14
   const float scale = 1.0f / sqrtf((float)hd);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& w = e->layers[l];
+    prof_mark(e, OASR_PROF_LAYERNORM, st);
     OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.attn_ln_g, w.attn_ln_b, e->lnbuf, nullptr, st));
+    prof_mark(e, OASR_PROF_QKV, st);
     {
       GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.wqkv, 3 * d);
       a.bias = w.bqkv;
@@ -371,7 +407,9 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
       a.epilogue = EPI_BF16;
       OASR_TRY(gemm_bf16_tcgen05(a, st));
     }
+    prof_mark(e, OASR_PROF_ATTENTION, st);
     OASR_TRY(attention_bf16(e->qkv, e->att, e->n_frames_dev, B, T, H, hd, scale, st));
+    prof_mark(e, OASR_PROF_OUTPROJ, st);
     {
       GemmArgs a = GemmArgs::plain(e->att, (int)M, d, d, w.wo, d);
       a.bias = w.bo;
@@ -381,7 +419,9 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
       a.epilogue = EPI_F32_RESID;
       OASR_TRY(gemm_bf16_tcgen05(a, st));
     }
+    prof_mark(e, OASR_PROF_LAYERNORM, st);
     OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.ffn_ln_g, w.ffn_ln_b, e->lnbuf, nullptr, st));
+    prof_mark(e, OASR_PROF_FFN1, st);
     {
       GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.w1, F);
       a.bias = w.b1;
@@ -390,6 +430,7 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
       a.epilogue = EPI_BF16_GELU;
       OASR_TRY(gemm_bf16_tcgen05(a, st));
     }
+    prof_mark(e, OASR_PROF_FFN2, st);
     {
       GemmArgs a = GemmArgs::plain(e->ffn, (int)M, F, F, w.w2, d);
       a.bias = w.b2;
@@ -400,9 +441,14 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
       OASR_TRY(gemm_bf16_tcgen05(a, st));
     }
     e->launches += 7;
-    if (stop_stage == 4 + l) return OASR_OK;
+    if (stop_stage == 4 + l) {
+      prof_mark(e, OASR_PROF_END, st);
+      return OASR_OK;
+    }
   }
+  prof_mark(e, OASR_PROF_LAYERNORM, st);
   OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
+  prof_mark(e, OASR_PROF_CTC_HEAD, st);
   // a15: logits stay in TMEM; only a packed (max, index) key per frame reaches HBM
   OASR_CUDA_CHECK(cudaMemsetAsync(e->keys, 0, (size_t)M * 8, st));
   {
@@ -413,8 +459,10 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
     OASR_TRY(gemm_bf16_tcgen05(a, st));
   }
   // a16
+  prof_mark(e, OASR_PROF_DECODE, st);
   OASR_TRY(ctc_decode(e->keys, e->n_frames_dev, B, T, c.blank_id, e->frame_ids, e->out_ids, e->out_frames, e->out_lens, st));
   e->launches += 4;
+  prof_mark(e, OASR_PROF_END, st);
   return OASR_OK;
 }
 
@@ -473,6 +521,8 @@ void oasr_destroy(OasrHandle h) {
   for (void* p : h->ws_owned) cudaFree(p);
   if (h->h_stage) cudaFreeHost(h->h_stage);
   for (cudaEvent_t ev : h->stage_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& m : h->prof_marks) cudaEventDestroy(m.second);
+  for (cudaEvent_t ev : h->prof_pool) cudaEventDestroy(ev);
   delete h;
 }
 
@@ -718,6 +768,35 @@ int oasr_debug_buffer(OasrHandle h, const char* name, void** dev_ptr, int64_t* s
 }
 
 int64_t oasr_launch_count(OasrHandle h) { return h ? h->launches : 0; }
+
+int oasr_profile_enable(OasrHandle h, int32_t on) {
+  OASR_REQUIRE(h, "oasr_profile_enable: null handle");
+  h->profiling = on != 0;
+  return OASR_OK;
+}
+
+int oasr_profile_read(OasrHandle h, double* ms, int64_t* counts, int32_t n) {
+  OASR_REQUIRE(h && ms && counts && n >= OASR_PROF_NCAT, "oasr_profile_read: need OASR_PROF_NCAT entries");
+  OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (size_t i = 0; i + 1 < h->prof_marks.size(); ++i) {
+    const int cat = h->prof_marks[i].first;
+    if (cat == OASR_PROF_END) continue;
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, h->prof_marks[i].second, h->prof_marks[i + 1].second) == cudaSuccess) {
+      h->prof_ms[cat] += t;
+      h->prof_n[cat] += 1;
+    }
+  }
+  for (auto& m : h->prof_marks) h->prof_pool.push_back(m.second);
+  h->prof_marks.clear();
+  for (int i = 0; i < OASR_PROF_NCAT; ++i) {
+    ms[i] = h->prof_ms[i];
+    counts[i] = h->prof_n[i];
+    h->prof_ms[i] = 0;
+    h->prof_n[i] = 0;
+  }
+  return OASR_OK;
+}
 
 // ---- per-stage entry points ---------------------------------------------------------------------------
 int oasr_wave_norm(const float* in, float* out, const int32_t* n_samples_dev, int32_t B, int32_t L, OasrStream stream) {

@@ -55,7 +55,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int UMMA_N = BN > 256 ? 256 : BN;
-  static constexpr int BAR_BYTES = 1024;
+  static constexpr int BAR_BYTES = 4096;  // barriers (<256 B) + LN reduction scratch (2 KB at +256)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
 };
 

@@ -17,6 +17,8 @@ ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = -1, -2, -3, -4
 DTYPE_F32, DTYPE_BF16 = 0, 1
 EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_ARGMAX, EPI_LN_GELU_BF16, EPI_F32_GELU_RESID = range(7)
 FLAG_INPUT_NORMALISED = 1
+PROF_CATEGORIES = ("wave_norm", "fe_layer0", "fe_conv_1_6", "layernorm", "feature_proj", "posconv", "qkv_gemm",
+                   "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "ctc_head_argmax", "decode", "end")
 
 
 class OasrConfig(C.Structure):
@@ -43,6 +45,8 @@ _PROTOTYPES = {
     "oasr_debug_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
     "oasr_debug_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
     "oasr_launch_count": (_i64, [_vp]),
+    "oasr_profile_enable": (C.c_int, [_vp, _i32]),
+    "oasr_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
     "oasr_wave_norm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "oasr_fe_layer0": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_conv_ln_gelu": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),

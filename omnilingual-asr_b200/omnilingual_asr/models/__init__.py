@@ -1,0 +1,7 @@
+"""Omnilingual ASR models."""
+
+from omnilingual_asr.models import inference as inference
+
+__all__ = [
+    "inference",
+]

@@ -189,6 +189,18 @@ class CtcEngine:
             raise RuntimeError(f"cudaMemcpy of debug buffer {name} failed: {rc}")
         return out
 
+    def profile(self, on: bool) -> None:
+        N.check(self._lib.oasr_profile_enable(self._handle, 1 if on else 0), "oasr_profile_enable")
+
+    def profile_read(self) -> dict:
+        """{stage: (milliseconds, launches)} accumulated since the last read (device time, CUDA events)."""
+        n = len(N.PROF_CATEGORIES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_profile_read(self._handle, ms, cnt, n), "oasr_profile_read")
+        return {N.PROF_CATEGORIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n) if N.PROF_CATEGORIES[i] != "end"}
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.oasr_launch_count(self._handle))

@@ -1,0 +1,296 @@
+"""CTC engine-level pipeline: the local replacement of the reference's GeminiASRPipeline.
+
+Mirrors src/omnilingual_asr/models/inference/gemini_pipeline.py of the reference:
+  * dataclasses CTCTranscriptSegment / CTCTranscriptionResult  <- GeminiTranscriptSegment / -Result (:47-70)
+  * transcribe / transcribe_chunked / transcribe_with_retry      <- :474-539, :577-682, :684-741
+  * window law (fixed, non-overlapping, start = i * window)      <- split_audio_into_chunks :243-310
+  * timestamp rebase by the window start                         <- _transcribe_chunk :555-569
+  * merge = windows in start order, segments concatenated        <- :646-654
+  * progress steps ("uploading",0) ("transcribing",1) ("processing",2) ("done",3)   <- :486-487
+  * errors: ValueError for configuration, RuntimeError("Failed to transcribe after N attempts: ...")
+    after retries (:329-334, :739-741)
+The per-chunk HTTPS call (:512-530) is replaced by CtcEngine.transcribe_host -> liboasr (sm_100a).
+Unlike the reference a failed window is never dropped silently (:635-641): a CUDA failure raises.
+"""
+from __future__ import annotations
+
+import threading
+import time
+from dataclasses import dataclass, field
+from pathlib import Path
+from typing import Any, Callable, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from omnilingual_asr.models.config import SAMPLE_RATE, CtcModelConfig, get_model_config
+from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, shard_range,
+                                                    split_into_windows, to_mono_16k)
+from omnilingual_asr.models.inference.tokenizer import CtcVocabulary
+
+# Window constants (the reference's CHUNK_DURATION_SECONDS / MIN_DURATION_FOR_CHUNKING / MAX_PARALLEL_CHUNKS,
+# gemini_pipeline.py:217-219, re-valued for the CTC models: upstream caps one input at 40 s).
+CHUNK_DURATION_SECONDS = 30.0
+MIN_DURATION_FOR_CHUNKING = 30.0
+MAX_ALLOWED_AUDIO_SEC = 40.0
+MAX_PARALLEL_CHUNKS = 32          # windows per device step (batch), not threads
+DEFAULT_SPEAKER = "Speaker 1"     # gemini_pipeline.py:435
+
+
+@dataclass(frozen=True)
+class WordTimestamp:
+    """Word-level timestamp information (gemini_pipeline.py:39-45)."""
+    word: str
+    start: float
+    end: float
+
+
+@dataclass
+class CTCTranscriptSegment:
+    """One transcribed segment; field-for-field GeminiTranscriptSegment (gemini_pipeline.py:47-61)."""
+    start: float
+    end: float
+    speaker: str
+    text: str
+    language: Optional[str] = None
+    language_code: Optional[str] = None
+    languages: Optional[List[dict]] = None
+    emotion: Optional[str] = None
+    translation: Optional[str] = None
+    words: Optional[List[WordTimestamp]] = None
+
+
+@dataclass
+class CTCTranscriptionResult:
+    """Complete result; mirrors GeminiTranscriptionResult (gemini_pipeline.py:64-70)."""
+    summary: Optional[str] = None
+    segments: List[CTCTranscriptSegment] = field(default_factory=list)
+    detected_languages: Optional[List[dict]] = None
+
+
+@dataclass
+class WindowTokens:
+    """Decoded tokens of one window, before text shaping (what travels between ranks)."""
+    index: int
+    start_sample: int
+    n_samples: int
+    n_frames: int
+    token_ids: np.ndarray
+    token_frames: np.ndarray
+
+
+AudioInput = Any  # path | np.ndarray | torch.Tensor | {"waveform": ..., "sample_rate": ...}
+
+
+def _resolve_audio(audio: AudioInput, sample_rate: Optional[int]) -> np.ndarray:
+    """Anything the boundary accepts -> mono float32 at 16 kHz."""
+    if isinstance(audio, (str, Path)):
+        return load_audio_16k(audio)
+    if isinstance(audio, Mapping):
+        return _resolve_audio(audio["waveform"], int(audio.get("sample_rate", sample_rate or SAMPLE_RATE)))
+    if hasattr(audio, "detach"):  # torch.Tensor
+        audio = audio.detach().cpu().float().numpy()
+    x = np.asarray(audio)
+    if x.dtype == np.int16:
+        x = x.astype(np.float32) / 32768.0
+    if x.ndim == 2 and x.shape[0] < x.shape[1] and x.shape[0] <= 8:
+        x = x.T  # [channels, n] -> [n, channels]
+    return to_mono_16k(x, int(sample_rate or SAMPLE_RATE))
+
+
+def build_segments(win: WindowTokens, vocab: CtcVocabulary, *, word_timestamps: bool,
+                   split_gap_sec: Optional[float], language: Optional[str]) -> List[CTCTranscriptSegment]:
+    """Tokens of one window -> segments with absolute times (rebase = gemini_pipeline.py:555-569).
+
+    Frame t of a window starts at window_start + t * (window_duration / n_frames); a segment runs from its
+    first token's frame to the end of its last token's frame.  With split_gap_sec the window is cut where no
+    token is emitted for at least that long (step *after* the path).
+    """
+    if win.n_frames <= 0 or len(win.token_ids) == 0:
+        return []
+    offset = win.start_sample / SAMPLE_RATE
+    frame_dur = (win.n_samples / SAMPLE_RATE) / win.n_frames
+    ids, frames = win.token_ids, win.token_frames
+    cuts = [0]
+    if split_gap_sec is not None and split_gap_sec > 0:
+        gap_frames = split_gap_sec / frame_dur
+        for i in range(1, len(frames)):
+            if frames[i] - frames[i - 1] >= gap_frames:
+                cuts.append(i)
+    cuts.append(len(ids))
+    out: List[CTCTranscriptSegment] = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        text = vocab.decode(ids[lo:hi])
+        if not text:
+            continue
+        words = None
+        if word_timestamps:
+            words = [WordTimestamp(w, offset + f0 * frame_dur, offset + (f1 + 1) * frame_dur)
+                     for (w, f0, f1) in vocab.words_with_frames(ids[lo:hi], frames[lo:hi])]
+        out.append(CTCTranscriptSegment(
+            start=offset + float(frames[lo]) * frame_dur,
+            end=offset + (float(frames[hi - 1]) + 1.0) * frame_dur,
+            speaker=DEFAULT_SPEAKER, text=text, language_code=language, words=words))
+    return out
+
+
+def merge_window_results(per_window: Sequence[Tuple[WindowTokens, List[CTCTranscriptSegment]]],
+                         language: Optional[str]) -> CTCTranscriptionResult:
+    """Sort by window start and concatenate (gemini_pipeline.py:646-678)."""
+    ordered = sorted(per_window, key=lambda r: r[0].start_sample)
+    segments: List[CTCTranscriptSegment] = []
+    for _, segs in ordered:
+        segments.extend(segs)
+    n_tok = sum(len(w.token_ids) for w, _ in ordered)
+    dur = sum(w.n_samples for w, _ in ordered) / SAMPLE_RATE
+    summary = f"{len(segments)} segment(s), {n_tok} token(s), {dur:.2f} s of audio in {len(ordered)} window(s)"
+    langs = [{"name": language, "code": language}] if language else None
+    return CTCTranscriptionResult(summary=summary, segments=segments, detected_languages=langs)
+
+
+class CTCASRPipeline:
+    """Local CTC pipeline with the reference engine's surface (GeminiASRPipeline, gemini_pipeline.py:313-741)."""
+
+    def __init__(self, model_card: str | CtcModelConfig = "omniASR_CTC_1B", *,
+                 weights: Any = None, vocabulary: Optional[CtcVocabulary | Sequence[str]] = None,
+                 device: Any = None, engine: Any = None, window_seconds: float = CHUNK_DURATION_SECONDS,
+                 batch_windows: int = MAX_PARALLEL_CHUNKS, split_gap_sec: Optional[float] = None,
+                 seed: int = 0, distributed: bool = True) -> None:
+        self.cfg = get_model_config(model_card)
+        if not (0 < window_seconds <= MAX_ALLOWED_AUDIO_SEC):
+            raise ValueError(f"window_seconds must be in (0, {MAX_ALLOWED_AUDIO_SEC}]")
+        if batch_windows <= 0:
+            raise ValueError("batch_windows must be positive")
+        self.window_samples = int(round(window_seconds * SAMPLE_RATE))
+        self.batch_windows = int(batch_windows)
+        self.split_gap_sec = split_gap_sec
+        self.distributed = distributed
+        if vocabulary is None:
+            vocabulary = CtcVocabulary.synthetic(self.cfg.vocab)
+        elif not isinstance(vocabulary, CtcVocabulary):
+            vocabulary = CtcVocabulary(list(vocabulary))
+        if len(vocabulary) != self.cfg.vocab:
+            raise ValueError(f"vocabulary has {len(vocabulary)} entries, model expects {self.cfg.vocab}")
+        self.vocab = vocabulary
+        self._lock = threading.Lock()   # one GPU submission at a time (app.py shares one pipeline over 4 threads)
+        if engine is not None:
+            self.engine = engine
+        else:
+            if weights is None:
+                raise ValueError(
+                    "no weights given: pass weights=<state dict | path to a torch checkpoint> or weights='random' "
+                    "(deterministic random init; there are no omniASR checkpoints offline)")
+            from omnilingual_asr.models.inference.ctc_engine import CtcEngine  # needs liboasr.so + CUDA
+            from omnilingual_asr.models.weights import resolve_weights
+            self.engine = CtcEngine(self.cfg, device=device)
+            self.engine.load_state_dict(resolve_weights(self.cfg, weights, seed, self.engine.device))
+
+    # ------------------------------------------------------------------ device step
+    def _rank_world(self) -> Tuple[int, int]:
+        if not self.distributed:
+            return 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                return dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        return 0, 1
+
+    def _run_windows(self, wave: np.ndarray, windows: List[Tuple[int, int]], lo: int, hi: int) -> List[WindowTokens]:
+        """Windows [lo, hi) through the engine in batches; host buffers in, token ids out."""
+        out: List[WindowTokens] = []
+        for b0 in range(lo, hi, self.batch_windows):
+            idx = list(range(b0, min(hi, b0 + self.batch_windows)))
+            L = max(windows[i][1] for i in idx)
+            batch = np.zeros((len(idx), L), dtype=np.float32)
+            for r, i in enumerate(idx):
+                s, n = windows[i]
+                batch[r, :n] = wave[s:s + n]
+            ns = [windows[i][1] for i in idx]
+            with self._lock:
+                res = self.engine.transcribe_host(batch, ns)
+            for r, i in enumerate(idx):
+                out.append(WindowTokens(i, windows[i][0], windows[i][1], int(res.n_frames[r]),
+                                        np.asarray(res.token_ids[r], dtype=np.int32),
+                                        np.asarray(res.token_frames[r], dtype=np.int32)))
+        return out
+
+    def _transcribe_wave(self, wave: np.ndarray, *, progress_callback, language, word_timestamps,
+                         chunked: bool) -> CTCTranscriptionResult:
+        def _report(step: str, idx: int) -> None:
+            if progress_callback:
+                progress_callback(step, idx)
+
+        if not chunked and len(wave) > int(MAX_ALLOWED_AUDIO_SEC * SAMPLE_RATE):
+            raise ValueError(f"audio longer than {MAX_ALLOWED_AUDIO_SEC} s needs chunking "
+                             "(use transcribe_chunked / transcribe_with_retry)")
+        windows = split_into_windows(len(wave), self.window_samples if chunked else max(len(wave), 1))
+        _report("transcribing", 1)
+        rank, world = self._rank_world()
+        lo, hi = shard_range(len(windows), rank, world)
+        mine = self._run_windows(wave, windows, lo, hi)
+        if world > 1:
+            import torch.distributed as dist
+            gathered: List[Optional[List[WindowTokens]]] = [None] * world
+            dist.all_gather_object(gathered, mine)      # host-side gather of token ids only
+            mine = [w for part in gathered for w in (part or [])]
+        _report("processing", 2)
+        shaped = [(w, build_segments(w, self.vocab, word_timestamps=word_timestamps,
+                                     split_gap_sec=self.split_gap_sec, language=language)) for w in mine]
+        result = merge_window_results(shaped, language)
+        _report("done", 3)
+        return result
+
+    # ------------------------------------------------------------------ reference surface
+    def transcribe(self, audio_path: AudioInput, *, progress_callback: Optional[Callable[[str, int], None]] = None,
+                   language: Optional[str] = None, speaker_count: Optional[str] = None,
+                   sample_rate: Optional[int] = None, word_timestamps: bool = False) -> CTCTranscriptionResult:
+        """One window (<= 40 s), no chunking: GeminiASRPipeline.transcribe (gemini_pipeline.py:474-539)."""
+        if progress_callback:
+            progress_callback("uploading", 0)
+        wave = _resolve_audio(audio_path, sample_rate)
+        return self._transcribe_wave(wave, progress_callback=progress_callback, language=language,
+                                     word_timestamps=word_timestamps, chunked=False)
+
+    def transcribe_chunked(self, audio_path: AudioInput, *,
+                           progress_callback: Optional[Callable[[str, int], None]] = None,
+                           language: Optional[str] = None, speaker_count: Optional[str] = None,
+                           sample_rate: Optional[int] = None, word_timestamps: bool = False) -> CTCTranscriptionResult:
+        """Long audio: fixed windows, batched over the device(s), merged in order (gemini_pipeline.py:577-682)."""
+        if progress_callback:
+            progress_callback("uploading", 0)
+        wave = _resolve_audio(audio_path, sample_rate)
+        return self._transcribe_wave(wave, progress_callback=progress_callback, language=language,
+                                     word_timestamps=word_timestamps, chunked=True)
+
+    def transcribe_with_retry(self, audio_path: AudioInput, *, max_retries: int = 3,
+                              progress_callback: Optional[Callable[[str, int], None]] = None,
+                              language: Optional[str] = None, speaker_count: Optional[str] = None,
+                              sample_rate: Optional[int] = None, word_timestamps: bool = False) -> CTCTranscriptionResult:
+        """Chunk iff the audio is longer than one window, retry runtime failures with 2^n backoff
+        (gemini_pipeline.py:684-741).  Configuration/input errors (ValueError, FileNotFoundError) are not
+        retried: a second attempt cannot change them."""
+        if progress_callback:
+            progress_callback("uploading", 0)
+        wave = _resolve_audio(audio_path, sample_rate)
+        duration = len(wave) / SAMPLE_RATE
+        use_chunking = duration > min(MIN_DURATION_FOR_CHUNKING, self.window_samples / SAMPLE_RATE)
+        last_error: Optional[BaseException] = None
+        for attempt in range(max_retries):
+            try:
+                return self._transcribe_wave(wave, progress_callback=progress_callback, language=language,
+                                             word_timestamps=word_timestamps, chunked=use_chunking)
+            except (ValueError, FileNotFoundError):
+                raise
+            except Exception as e:  # noqa: BLE001 - mirrors the reference's catch-all
+                last_error = e
+                if attempt < max_retries - 1:
+                    time.sleep(2 ** attempt)
+        raise RuntimeError(f"Failed to transcribe after {max_retries} attempts: {last_error}")
+
+
+__all__ = [
+    "CTCASRPipeline", "CTCTranscriptionResult", "CTCTranscriptSegment", "WordTimestamp", "WindowTokens",
+    "build_segments", "merge_window_results", "get_audio_duration", "split_into_windows",
+    "CHUNK_DURATION_SECONDS", "MIN_DURATION_FOR_CHUNKING", "MAX_PARALLEL_CHUNKS", "MAX_ALLOWED_AUDIO_SEC",
+]

@@ -85,7 +85,7 @@ PRESETS: Dict[str, CtcModelConfig] = {
     "omniASR_CTC_7B": CtcModelConfig("omniASR_CTC_7B", 2048, 128, 16, 8192),
     # Small shapes for fast parity tests; same graph, legal tensor-core shapes.
     "tiny": CtcModelConfig("tiny", 256, 2, 4, 512, vocab=300),
-    "tiny80": CtcModelConfig("tiny80", 320, 2, 4, 640, vocab=1000),
+    "tiny80": CtcModelConfig("tiny80", 320, 2, 4, 640, vocab=500, pos_groups=4),   # head_dim 80, group width 80 (1B-like)
 }
 
 PUBLISHED_PARAM_COUNTS = {

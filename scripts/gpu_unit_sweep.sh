@@ -6,7 +6,8 @@ mkdir -p gpurun_out
 OUT=gpurun_out/unit_sweep.log
 : > $OUT
 nvidia-smi --query-gpu=name,driver_version,memory.total --format=csv >> $OUT 2>&1
-TESTS=$(python -m pytest $FILE -m gpu --collect-only -q 2>/dev/null | grep "::" )
+# one process per test function (all its parametrisations together)
+TESTS=$(python -m pytest $FILE -m gpu --collect-only -q 2>/dev/null | grep "::" | sed 's/\[.*//' | sort -u)
 for t in $TESTS; do
   echo "=== $t" >> $OUT
   timeout 300 python -m pytest "$t" -q -m gpu -x --no-header -p no:cacheprovider 2>&1 | tail -25 >> $OUT
