@@ -112,6 +112,8 @@ OASR_API int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t 
 OASR_API int oasr_debug_forward(OasrHandle h, const float* wave_dev, int64_t wave_stride, const int32_t* n_samples_host,
                        int32_t B, int32_t L, int32_t flags, int32_t stop_stage, OasrStream stream);
 OASR_API int oasr_debug_buffer(OasrHandle h, const char* name, void** dev_ptr, int64_t* shape4, int32_t* dtype);
+/* Device-to-device copy of `nbytes` of a named internal buffer into dst_dev (synchronous). */
+OASR_API int oasr_debug_copy(OasrHandle h, const char* name, void* dst_dev, int64_t nbytes);
 
 /* Kernel launches issued by this handle since creation (bench.py reports it as gpu_launches). */
 OASR_API int64_t oasr_launch_count(OasrHandle h);

@@ -767,6 +767,20 @@ int oasr_debug_buffer(OasrHandle h, const char* name, void** dev_ptr, int64_t* s
   return OASR_OK;
 }
 
+int oasr_debug_copy(OasrHandle h, const char* name, void* dst_dev, int64_t nbytes) {
+  void* src = nullptr;
+  int64_t shape[4];
+  int32_t dt = 0;
+  OASR_TRY(oasr_debug_buffer(h, name, &src, shape, &dt));
+  OASR_REQUIRE(dst_dev && nbytes >= 0, "oasr_debug_copy: bad destination");
+  int64_t have = dt == OASR_DTYPE_BF16 ? 2 : 4;
+  for (int i = 0; i < 4 && shape[i] > 0; ++i) have *= shape[i];
+  OASR_REQUIRE(nbytes <= have, "oasr_debug_copy: more bytes requested than the buffer holds");
+  OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  OASR_CUDA_CHECK(cudaMemcpy(dst_dev, src, (size_t)nbytes, cudaMemcpyDeviceToDevice));
+  return OASR_OK;
+}
+
 int64_t oasr_launch_count(OasrHandle h) { return h ? h->launches : 0; }
 
 int oasr_profile_enable(OasrHandle h, int32_t on) {

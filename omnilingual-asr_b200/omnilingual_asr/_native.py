@@ -44,6 +44,7 @@ _PROTOTYPES = {
     "oasr_transcribe_host": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "oasr_debug_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
     "oasr_debug_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
+    "oasr_debug_copy": (C.c_int, [_vp, C.c_char_p, _vp, _i64]),
     "oasr_launch_count": (_i64, [_vp]),
     "oasr_profile_enable": (C.c_int, [_vp, _i32]),
     "oasr_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),

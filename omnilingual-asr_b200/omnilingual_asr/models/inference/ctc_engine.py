@@ -184,9 +184,8 @@ class CtcEngine:
         dtype = torch.bfloat16 if dt.value == N.DTYPE_BF16 else torch.float32
         out = torch.empty(dims, dtype=dtype, device=self.device)
         nbytes = out.numel() * out.element_size()
-        rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), p.value, nbytes, 3)  # 3 = DeviceToDevice
-        if int(rc) != 0:
-            raise RuntimeError(f"cudaMemcpy of debug buffer {name} failed: {rc}")
+        with torch.cuda.device(self.device):
+            N.check(self._lib.oasr_debug_copy(self._handle, name.encode(), N.ptr(out), nbytes), "oasr_debug_copy")
         return out
 
     def profile(self, on: bool) -> None:

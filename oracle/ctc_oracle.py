@@ -268,7 +268,7 @@ def forward(w: Dict[str, torch.Tensor], wave: torch.Tensor, n_samples: Sequence[
     n_frames = [feature_length(int(n), cfg) for n in n_samples]
     tp: Dict[str, torch.Tensor] = {}
 
-    feats = feature_extractor(w, wave, cfg, q)          # [B, T, 512]
+    feats = _q(feature_extractor(w, wave, cfg, q), q)   # [B, T, 512]; the engine keeps FE activations in bf16
     T = feats.shape[1]
     if taps:
         tp["fe"] = feats.clone()

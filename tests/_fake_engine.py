@@ -1,0 +1,46 @@
+"""Test double for CtcEngine: same `transcribe_host` contract, computed by the CPU oracle.
+
+Lives under tests/ only, so host logic (chunking, batching, merging, sharding) can be exercised without a GPU.
+The product path never imports this."""
+import numpy as np
+import torch
+
+from omnilingual_asr.models.config import CtcModelConfig
+from omnilingual_asr.models.inference.ctc_engine import CtcBatchResult
+from oracle import ctc_oracle as O
+
+
+class OracleEngine:
+    def __init__(self, name="tiny", seed=0):
+        self.ocfg = O.PRESETS[name]
+        self.cfg = CtcModelConfig(self.ocfg.name, self.ocfg.d_model, self.ocfg.n_layers, self.ocfg.n_heads,
+                                  self.ocfg.d_ffn, vocab=self.ocfg.vocab, pos_groups=self.ocfg.pos_groups)
+        self.w = O.init_weights(self.ocfg, seed)
+        self.device = torch.device("cpu")
+        self.calls = []
+
+    def transcribe_host(self, wave, n_samples, *, normalised=False, return_frame_ids=False):
+        wave = torch.as_tensor(np.asarray(wave), dtype=torch.float32)
+        self.calls.append((tuple(wave.shape), list(n_samples)))
+        if not normalised:
+            wave = O.wave_layer_norm(wave, n_samples)
+        out = O.forward(self.w, wave, n_samples, self.ocfg)
+        ids, frames = [], []
+        for b, nf in enumerate(out.n_frames):
+            i, p = O.greedy_collapse(out.frame_ids[b], nf)
+            ids.append(np.array(i, dtype=np.int32))
+            frames.append(np.array(p, dtype=np.int32))
+        return CtcBatchResult(ids, frames, out.n_frames, out.frame_ids.numpy() if return_frame_ids else None)
+
+
+class FlakyEngine(OracleEngine):
+    """Fails the first `fail` calls with a RuntimeError (retry path)."""
+    def __init__(self, fail, **kw):
+        super().__init__(**kw)
+        self.fail = fail
+
+    def transcribe_host(self, *a, **kw):
+        if self.fail > 0:
+            self.fail -= 1
+            raise RuntimeError("injected device failure")
+        return super().transcribe_host(*a, **kw)

@@ -18,6 +18,7 @@ for p in (str(ROOT), str(PKG)):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    config.addinivalue_line("markers", "slow: several seconds of CPU work")
 
 
 @pytest.fixture(scope="session")

@@ -1,0 +1,56 @@
+"""N>1 path on the CPU: two gloo ranks shard the windows, gather token ids on the host, and every rank ends
+with the result of the single-process run."""
+import os
+import pickle
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (str(ROOT), str(ROOT / "omnilingual-asr_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    from omnilingual_asr import CTCASRPipeline
+    from tests._fake_engine import OracleEngine
+    torch.set_num_threads(2)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = OracleEngine("tiny")
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=2)
+    x = np.random.default_rng(9).standard_normal(int(5.3 * 16000)).astype(np.float32)
+    res = pipe.transcribe_chunked(x)
+    windows_here = sum(c[0][0] for c in eng.calls)
+    with open(os.path.join(out_dir, f"r{rank}.pkl"), "wb") as f:
+        pickle.dump(([(s.start, s.end, s.text) for s in res.segments], windows_here), f)
+    dist.destroy_process_group()
+
+
+def test_two_rank_shard_and_host_gather(tmp_path):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [pickle.load(open(tmp_path / f"r{r}.pkl", "rb")) for r in range(world)]
+    assert outs[0][0] == outs[1][0]                       # every rank holds the merged transcript
+    assert outs[0][1] + outs[1][1] == 6 and abs(outs[0][1] - outs[1][1]) <= 1   # 6 windows, block partition
+    # equals the single-process result
+    for p in (str(ROOT), str(ROOT / "omnilingual-asr_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from omnilingual_asr import CTCASRPipeline
+    from tests._fake_engine import OracleEngine
+    eng = OracleEngine("tiny")
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=2, distributed=False)
+    x = np.random.default_rng(9).standard_normal(int(5.3 * 16000)).astype(np.float32)
+    single = [(s.start, s.end, s.text) for s in pipe.transcribe_chunked(x).segments]
+    assert single == outs[0][0]
+    starts = [s[0] for s in single]
+    assert starts == sorted(starts)

@@ -1,0 +1,205 @@
+"""Host-side logic behind the reference's pipeline API, on the CPU with an oracle-backed engine double."""
+import threading
+import wave as wavelib
+
+import numpy as np
+import pytest
+
+import omnilingual_asr
+from omnilingual_asr import CTCASRPipeline, CTCTranscriptionPipeline, DiarizedTranscriptSegment, WordTimestamp
+from omnilingual_asr.models.inference import ctc_pipeline as P
+from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, read_wav, shard_range,
+                                                    split_into_windows, to_mono_16k)
+from omnilingual_asr.models.inference.pipeline import ASRInferencePipeline
+from omnilingual_asr.models.inference.tokenizer import WORD_BOUNDARY, CtcVocabulary
+from oracle import ctc_oracle as O
+from tests._fake_engine import FlakyEngine, OracleEngine
+
+
+def noise(seconds, seed=0, sr=16000):
+    return np.random.default_rng(seed).standard_normal(int(seconds * sr)).astype(np.float32)
+
+
+@pytest.fixture(scope="module")
+def engine():
+    return OracleEngine("tiny")
+
+
+def test_public_names_and_version():
+    assert omnilingual_asr.__version__ == "0.2.0"
+    for n in ("CTCASRPipeline", "CTCTranscriptionResult", "CTCTranscriptSegment", "CTCTranscriptionPipeline",
+              "DiarizedTranscriptSegment", "WordTimestamp"):
+        assert hasattr(omnilingual_asr, n)
+    seg = DiarizedTranscriptSegment(0.0, 1.0, "Speaker 1", "hi")
+    assert (seg.words, seg.language, seg.language_code, seg.languages, seg.emotion, seg.translation) == (None,) * 6
+    with pytest.raises(Exception):
+        seg.start = 2.0  # frozen, like the reference's record
+
+
+def test_constructor_errors_are_value_errors():
+    with pytest.raises(ValueError, match="no weights"):
+        CTCTranscriptionPipeline()
+    with pytest.raises(ValueError, match="unknown CTC model card"):
+        CTCASRPipeline("omniASR_CTC_9B", weights="random")
+    with pytest.raises(ValueError):
+        CTCASRPipeline("omniASR_CTC_1B", engine=object(), window_seconds=45)
+    with pytest.raises(ValueError, match="vocabulary"):
+        CTCASRPipeline(OracleEngine("tiny").cfg, engine=object(), vocabulary=["a", "b"])
+
+
+def test_window_law_matches_reference_chunker():
+    assert split_into_windows(0, 480000) == [(0, 0)]
+    w = split_into_windows(3600 * 16000, 480000)
+    assert len(w) == 120 and w[7] == (7 * 480000, 480000)
+    w = split_into_windows(34200 * 16000, 480000)
+    assert len(w) == 1140
+    w = split_into_windows(281233, 480000)
+    assert w == [(0, 281233)]
+    w = split_into_windows(1_000_000, 480000)
+    assert w == [(0, 480000), (480000, 480000), (960000, 40000)]
+    assert w == O.split_into_windows(1_000_000, 480000)
+
+
+def test_shard_ranges_cover_everything_in_order():
+    for n in (0, 1, 7, 120, 1140):
+        for world in (1, 2, 4, 8):
+            parts = [shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            assert max(hi - lo for lo, hi in parts) - min(hi - lo for lo, hi in parts) <= 1
+
+
+def test_wav_reader_and_resampler(tmp_path):
+    sr = 22050
+    t = np.arange(sr) / sr
+    x = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    st = np.stack([x, -x * 0.5], axis=1)
+    p = tmp_path / "a.wav"
+    with wavelib.open(str(p), "wb") as wf:
+        wf.setnchannels(2)
+        wf.setsampwidth(2)
+        wf.setframerate(sr)
+        wf.writeframes((st * 32767).astype("<i2").tobytes())
+    y, r = read_wav(p)
+    assert r == sr and y.shape == (sr, 2)
+    assert abs(get_audio_duration(p) - 1.0) < 1e-9
+    assert get_audio_duration(tmp_path / "missing.wav") == 0.0
+    m = load_audio_16k(p)
+    assert m.dtype == np.float32 and abs(len(m) - 16000) <= 1
+    assert np.allclose(to_mono_16k(x, 16000), x)
+    with pytest.raises(ValueError):
+        load_audio_16k(tmp_path / "a.mp3") if (tmp_path / "a.mp3").write_bytes(b"x") else None
+    with pytest.raises(FileNotFoundError):
+        load_audio_16k(tmp_path / "nope.wav")
+
+
+def test_tokenizer_decode_and_words():
+    v = CtcVocabulary.synthetic(300)
+    ids = [4, 5, 6, 4, 7, 0, 8]          # "▁ab▁cd" with a special in between
+    assert v.decode(ids) == "ab cd"
+    words = v.words_with_frames(ids, [0, 3, 5, 9, 11, 12, 20])
+    assert words == [("ab", 3, 5), ("cd", 11, 20)]
+    assert v.decode([0, 1, 2, 3]) == ""
+    assert len(v) == 300 and v.pieces[4] == WORD_BOUNDARY
+
+
+def test_single_window_segments_match_oracle(engine):
+    pipe = CTCASRPipeline(engine.cfg, engine=engine)
+    x = noise(3.0, 1)
+    res = pipe.transcribe(x, word_timestamps=True)
+    wave = O.wave_layer_norm(__import__("torch").from_numpy(x)[None], [len(x)])
+    out = O.forward(engine.w, wave, [len(x)], engine.ocfg)
+    ids, pos = O.greedy_collapse(out.frame_ids[0], out.n_frames[0])
+    assert len(res.segments) == 1
+    seg = res.segments[0]
+    assert seg.text == pipe.vocab.decode(ids)
+    fd = 3.0 / out.n_frames[0]
+    assert seg.start == pytest.approx(pos[0] * fd) and seg.end == pytest.approx((pos[-1] + 1) * fd)
+    assert seg.speaker == "Speaker 1" and seg.words is not None
+    assert all(isinstance(w, P.WordTimestamp) and seg.start <= w.start <= w.end <= seg.end + 1e-9 for w in seg.words)
+
+
+def test_long_audio_is_chunked_rebased_and_merged_in_order(engine):
+    pipe = CTCASRPipeline(engine.cfg, engine=engine, window_seconds=2.0, batch_windows=2)
+    x = noise(5.5, 2)
+    steps = []
+    res = pipe.transcribe_with_retry(x, progress_callback=lambda s, i: steps.append((s, i)))
+    assert steps == [("uploading", 0), ("transcribing", 1), ("processing", 2), ("done", 3)]
+    # 3 windows (2 s, 2 s, 1.5 s) in 2 device steps
+    assert [c[0][0] for c in engine.calls[-2:]] == [2, 1]
+    starts = [s.start for s in res.segments]
+    assert starts == sorted(starts) and len(res.segments) == 3
+    for i, seg in enumerate(res.segments):
+        assert 2.0 * i <= seg.start < seg.end <= min(2.0 * (i + 1), 5.5) + 1e-6
+    # each window equals the single-window transcription of the same samples, rebased by its start offset
+    for i, seg in enumerate(res.segments):
+        one = pipe.transcribe(x[i * 32000:(i + 1) * 32000]).segments[0]
+        assert one.text == seg.text
+        assert seg.start == pytest.approx(one.start + 2.0 * i)
+
+
+def test_too_long_for_unchunked_entry_point(engine):
+    pipe = CTCASRPipeline(engine.cfg, engine=engine)
+    with pytest.raises(ValueError, match="needs chunking"):
+        pipe.transcribe(np.zeros(41 * 16000, dtype=np.float32))
+
+
+def test_retry_then_success_and_exhaustion(monkeypatch):
+    monkeypatch.setattr(P.time, "sleep", lambda s: None)
+    eng = FlakyEngine(2, name="tiny")
+    pipe = CTCASRPipeline(eng.cfg, engine=eng)
+    assert pipe.transcribe_with_retry(noise(1.0)).segments
+    eng = FlakyEngine(5, name="tiny")
+    pipe = CTCASRPipeline(eng.cfg, engine=eng)
+    with pytest.raises(RuntimeError, match="Failed to transcribe after 3 attempts: injected device failure"):
+        pipe.transcribe_with_retry(noise(1.0))
+
+
+def test_boundary_pipeline_surface_and_thread_local_summary(engine, tmp_path):
+    pipe = CTCTranscriptionPipeline(model_card=engine.cfg, engine=engine)
+    assert pipe.summary is None and pipe.detected_languages is None
+    p = tmp_path / "x.wav"
+    with wavelib.open(str(p), "wb") as wf:
+        wf.setnchannels(1)
+        wf.setsampwidth(2)
+        wf.setframerate(16000)
+        wf.writeframes((np.clip(noise(1.5, 3) * 0.2, -1, 1) * 32767).astype("<i2").tobytes())
+    segs = pipe.transcribe(str(p), word_timestamps=True, language="en", speaker_count="2", unknown_kwarg=1)
+    assert segs and all(isinstance(s, DiarizedTranscriptSegment) for s in segs)
+    assert all(isinstance(w, WordTimestamp) for w in segs[0].words)
+    assert segs[0].language_code == "en" and pipe.detected_languages == [{"name": "en", "code": "en"}]
+    assert "segment" in pipe.summary
+    seen = {}
+
+    def worker(name, secs):
+        pipe.transcribe(noise(secs, 4))
+        seen[name] = pipe.summary
+
+    ts = [threading.Thread(target=worker, args=(i, 0.5 + 0.5 * i)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert all(f"{0.5 + 0.5 * i:.2f} s" in seen[i] for i in range(4))   # no cross-thread overwrite
+
+
+def test_asr_inference_pipeline_shim(engine):
+    shim = ASRInferencePipeline(model_card=engine.cfg, engine=engine)
+    a, b = noise(1.0, 5), noise(2.0, 6)
+    texts = shim.transcribe([a, {"waveform": b, "sample_rate": 16000}], batch_size=2)
+    pipe = CTCASRPipeline(engine.cfg, engine=engine)
+    # batched with zero padding == alone (the engine masks padded frames)
+    assert texts[1] == pipe.transcribe(b).segments[0].text
+    assert isinstance(texts[0], str)
+    with pytest.raises(ValueError):
+        shim.transcribe("not-a-list")
+    with pytest.raises(ValueError):
+        shim.transcribe([np.zeros(41 * 16000, dtype=np.float32)])
+
+
+def test_split_on_silence_shapes_segments():
+    v = CtcVocabulary.synthetic(300)
+    win = P.WindowTokens(0, 0, 480000, 1499, np.array([5, 6, 7, 8], np.int32), np.array([10, 12, 400, 405], np.int32))
+    one = P.build_segments(win, v, word_timestamps=False, split_gap_sec=None, language=None)
+    two = P.build_segments(win, v, word_timestamps=False, split_gap_sec=1.0, language=None)
+    assert len(one) == 1 and len(two) == 2 and two[0].text == "ab" and two[1].text == "cd"
+    assert P.build_segments(P.WindowTokens(0, 0, 100, 0, np.array([], np.int32), np.array([], np.int32)), v,
+                            word_timestamps=True, split_gap_sec=None, language=None) == []
