@@ -1,3 +1,5 @@
+// Attention, first version (two passes over the keys, P staged through shared memory).  Kept as the
+// reference implementation of the numerics contract; select with OASR_ATTN_V1=1.  See attention_v2.cu.
 // Bidirectional self-attention for one (sequence, head, 128-query tile) per CTA on tcgen05 (a14).
 //
 //   S = Q K^T   tcgen05.mma, A = Q tile, B = K tile, both K-major bf16 in 32B-swizzled 16-column chunks
@@ -287,7 +289,7 @@ std::mutex g_att_mu;
 
 }  // namespace
 
-int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+int attention_bf16_v1(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                    cudaStream_t stream) {
   OASR_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "attention: bad arguments");
   OASR_REQUIRE(hd % 16 == 0 && hd >= 16 && hd <= 128, "attention: head_dim must be a multiple of 16 in [16, 128]");

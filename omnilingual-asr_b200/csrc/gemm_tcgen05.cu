@@ -56,7 +56,8 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int UMMA_N = BN > 256 ? 256 : BN;
   static constexpr int BAR_BYTES = 4096;  // barriers (<256 B) + LN reduction scratch (2 KB at +256)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 20 * 4;  // per-warp [32][20] word transpose buffers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/;
 };
 
 struct TileCoord {
@@ -88,6 +89,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* red1 = reinterpret_cast<float*>(bar_base + 256);  // [2][128] LN partial sums
   float* red2 = red1 + 256;                                // [2][128]
+  constexpr int STAGE_LD = 20;                             // words per staged row: 16 payload + 4 pad (80 B)
+  uint32_t* stage = reinterpret_cast<uint32_t*>(bar_base + C::BAR_BYTES) + ((threadIdx.x >> 5) & 7) * (32 * STAGE_LD);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -202,6 +205,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
 
+      // Rows of this warp: [m0 + 32q, +32).  Global stores (and residual loads) go through a warp-private
+      // smem transpose so that one instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B.
+      const int rows_valid = min(32, max(0, p.rows_per_batch - (tc.m0 + q * 32)));
+      const long long out_row0 = (long long)tc.b * p.out_batch_rows + tc.m0 + q * 32;
+      const int t_r8 = lane & 7, t_piece = lane >> 3;   // transposed role: row-in-group, 16-byte piece
+
+      // store a [32 rows x 32 cols] bf16 chunk held row-per-thread as 16 packed words
+      auto store_bf16_chunk = [&](const uint32_t (&o)[16], int col0 /* within group */) {
+        uint4* srow = reinterpret_cast<uint4*>(stage + lane * STAGE_LD);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) srow[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        __syncwarp();
+        const int n = col0 + t_piece * 8;
+        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row0 * p.ldo + gcol + n;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + t_r8;
+          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * STAGE_LD + t_piece * 4);
+          if (row < rows_valid && n < p.N) *reinterpret_cast<uint4*>(obase + (long long)row * p.ldo) = val;
+        }
+        __syncwarp();
+      };
+
       if constexpr (EPI == EPI_LN_GELU_BF16) {
         // LayerNorm over the 512 channels of the row: 3 passes over TMEM, partner warp holds the other half.
         float s1 = 0.f;
@@ -232,7 +258,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         named_bar_sync(1 + q, 64);
         const float var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
         const float rstd = rsqrtf(var + 1e-5f);
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n_base;
 #pragma unroll 1
         for (int c = 0; c < HALF_N; c += 32) {
           uint32_t v[32];
@@ -248,11 +273,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             x1 = gelu_erf(x1 * __ldg(p.ln_gamma + n + 1) + __ldg(p.ln_beta + n + 1));
             o[j >> 1] = pack_bf16x2(x0, x1);
           }
-          if (row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(orow + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          }
+          store_bf16_chunk(o, n_base + c);
         }
       } else if constexpr (EPI == EPI_ARGMAX) {
         float best = -INFINITY;
@@ -268,7 +289,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int j = 0; j < 32; ++j) {
               const int n = n0 + j;
               if (n < p.N) {
-                const float x = __uint_as_float(v[j]) + __ldg(bias_g + n);
+                const float x = __uint_as_float(v[j]) + __ldg(p.bias + n);
                 if (x > best) {  // strict: lowest index wins among equals (torch.argmax)
                   best = x;
                   best_i = n;
@@ -278,78 +299,74 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         if (row_ok && best_i != 0x7fffffff) atomicMax(p.argmax + out_row, argmax_pack(best, best_i));
-      } else {
-        bool zero_row = false;
-        if constexpr (EPI == EPI_F32) {
-          if (p.n_valid != nullptr && row_ok) {
-            const int seq = int(out_row / p.frames_per_seq);
-            const int t = int(out_row - (long long)seq * p.frames_per_seq);
-            zero_row = t >= __ldg(p.n_valid + seq);
-          }
-        }
+      } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
 #pragma unroll 1
         for (int c = 0; c < HALF_N; c += 32) {
           uint32_t v[32];
           tmem_ld32(t_base + c, v);
           tmem_ld_wait();
           const int n0 = n_base + c;
-          if (row_ok && n0 < p.N) {
-            const bool full_chunk = (n0 + 32 <= p.N);
-            if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-              __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + gcol + n0;
-              if (full_chunk) {
-                uint32_t o[16];
+          if (n0 < p.N) {   // warp-uniform
+            uint32_t o[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  float x0 = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
-                  float x1 = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + n0 + j + 1) : 0.f);
-                  if constexpr (EPI == EPI_BF16_GELU) {
-                    x0 = gelu_erf(x0);
-                    x1 = gelu_erf(x1);
-                  }
-                  o[j >> 1] = pack_bf16x2(x0, x1);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(orow);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              } else {
-                for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-                  float x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
-                  if constexpr (EPI == EPI_BF16_GELU) x = gelu_erf(x);
-                  orow[j] = __float2bfloat16(x);
-                }
+            for (int j = 0; j < 32; j += 2) {
+              // columns >= N of a partial chunk hold zero accumulators; clamp the bias index, results are not stored
+              float x0 = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + min(n0 + j, p.N - 1)) : 0.f);
+              float x1 = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + min(n0 + j + 1, p.N - 1)) : 0.f);
+              if constexpr (EPI == EPI_BF16_GELU) {
+                x0 = gelu_erf(x0);
+                x1 = gelu_erf(x1);
               }
-            } else {  // fp32 outputs
-              float* orow = reinterpret_cast<float*>(p.out) + out_row * p.ldo + gcol + n0;
-              const float* rrow = nullptr;
-              if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) rrow = p.resid + out_row * p.ldo + gcol + n0;
-              if (full_chunk) {
+              o[j >> 1] = pack_bf16x2(x0, x1);
+            }
+            store_bf16_chunk(o, n0);
+          }
+        }
+      } else {
+        // fp32 outputs: EPI_F32 / EPI_F32_RESID / EPI_F32_GELU_RESID, 16 columns per transpose round
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_base + c, v);
+          tmem_ld_wait();
+          if (n_base + c < p.N) {   // warp-uniform
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  float4 x;
-                  x.x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
-                  x.y = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + n0 + j + 1) : 0.f);
-                  x.z = __uint_as_float(v[j + 2]) + (bias_g ? __ldg(bias_g + n0 + j + 2) : 0.f);
-                  x.w = __uint_as_float(v[j + 3]) + (bias_g ? __ldg(bias_g + n0 + j + 3) : 0.f);
+            for (int hh = 0; hh < 2; ++hh) {
+              float4* srow = reinterpret_cast<float4*>(stage + lane * STAGE_LD);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                srow[j] = make_float4(__uint_as_float(v[hh * 16 + 4 * j]), __uint_as_float(v[hh * 16 + 4 * j + 1]),
+                                      __uint_as_float(v[hh * 16 + 4 * j + 2]), __uint_as_float(v[hh * 16 + 4 * j + 3]));
+              __syncwarp();
+              const int n = n_base + c + hh * 16 + t_piece * 4;
+              const bool col_ok = n < p.N;
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias_g && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias_g + n));
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + t_r8;
+                float4 a = *reinterpret_cast<const float4*>(stage + row * STAGE_LD + t_piece * 4);
+                if (row < rows_valid && col_ok) {
+                  const long long grow = out_row0 + row;
+                  a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
                   if constexpr (EPI == EPI_F32_GELU_RESID) {
-                    x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+                    a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
                   }
                   if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) {
-                    const float4 rr = *reinterpret_cast<const float4*>(rrow + j);
-                    x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+                    const float4 rr = *reinterpret_cast<const float4*>(p.resid + grow * p.ldo + gcol + n);
+                    a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
                   }
-                  if (zero_row) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                  *reinterpret_cast<float4*>(orow + j) = x;
-                }
-              } else {
-                for (int j = 0; j < 32 && n0 + j < p.N; ++j) {
-                  float x = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + n0 + j) : 0.f);
-                  if constexpr (EPI == EPI_F32_GELU_RESID) x = gelu_erf(x);
-                  if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) x += rrow[j];
-                  if (zero_row) x = 0.f;
-                  orow[j] = x;
+                  if constexpr (EPI == EPI_F32) {
+                    if (p.n_valid != nullptr) {
+                      const int seq = int(grow / p.frames_per_seq);
+                      const int t = int(grow - (long long)seq * p.frames_per_seq);
+                      if (t >= __ldg(p.n_valid + seq)) a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                  }
+                  *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ldo + gcol + n) = a;
                 }
               }
+              __syncwarp();
             }
           }
         }

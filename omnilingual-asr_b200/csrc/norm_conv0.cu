@@ -172,7 +172,8 @@ fe_layer0_kernel(const float* __restrict__ wave, long long in_stride, int T0, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row LayerNorm: one warp per row, D = 64 * VEC2 * ... kept in registers.  D % 64 == 0, D <= 2048.
+// Row LayerNorm: one warp per row, the row lives in registers as float4 groups (lane owns groups
+// lane + 32 j).  D % 4 == 0, D <= 2048.  16-byte loads, 8/16-byte stores, two-pass fp32 statistics.
 // ---------------------------------------------------------------------------------------------
 template <bool IN_BF16>
 __global__ void __launch_bounds__(256)
@@ -185,50 +186,66 @@ layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int bat
   if (row >= total) return;
   const int b = int(row / rows_per_batch);
   const int t = int(row - (long long)b * rows_per_batch);
-  const int npairs = D >> 6;  // float2 per lane
-  float2 v[32];
+  const int ngroups = D >> 2;  // float4 groups in the row
+  constexpr int MAXJ = 16;
+  float4 v[MAXJ];
   float s = 0.f;
   if (IN_BF16) {
-    const __nv_bfloat162* p =
-        reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(in) + (long long)b * in_batch_stride +
-                                                (long long)t * D);
+    const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(in) +
+                                                    (long long)b * in_batch_stride + (long long)t * D);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < npairs) {
-        v[j] = __bfloat1622float2(p[lane + 32 * j]);
-        s += v[j].x + v[j].y;
+    for (int j = 0; j < MAXJ; ++j) {
+      const int g = lane + 32 * j;
+      if (g < ngroups) {
+        const uint2 u = __ldg(p + g);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+        v[j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        s += (lo.x + lo.y) + (hi.x + hi.y);
       }
+    }
   } else {
-    const float2* p = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(in) + (long long)b * in_batch_stride +
-                                                      (long long)t * D);
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) +
+                                                      (long long)b * in_batch_stride + (long long)t * D);
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < npairs) {
-        v[j] = p[lane + 32 * j];
-        s += v[j].x + v[j].y;
+    for (int j = 0; j < MAXJ; ++j) {
+      const int g = lane + 32 * j;
+      if (g < ngroups) {
+        v[j] = __ldg(p + g);
+        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
+    }
   }
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (j < npairs) {
-      v[j].x -= mean;
-      v[j].y -= mean;
-      q += v[j].x * v[j].x + v[j].y * v[j].y;
+  for (int j = 0; j < MAXJ; ++j)
+    if (lane + 32 * j < ngroups) {
+      v[j].x -= mean; v[j].y -= mean; v[j].z -= mean; v[j].w -= mean;
+      q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
-  const float2* g2 = reinterpret_cast<const float2*>(gamma);
-  const float2* b2 = reinterpret_cast<const float2*>(beta);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-  for (int j = 0; j < 32; ++j)
-    if (j < npairs) {
-      const float2 g = __ldg(g2 + lane + 32 * j), bb = __ldg(b2 + lane + 32 * j);
-      const float y0 = v[j].x * rstd * g.x + bb.x;
-      const float y1 = v[j].y * rstd * g.y + bb.y;
-      if (out_bf16) reinterpret_cast<uint32_t*>(out_bf16 + row * D)[lane + 32 * j] = pack_bf16x2(y0, y1);
-      if (out_f32) reinterpret_cast<float2*>(out_f32 + row * D)[lane + 32 * j] = make_float2(y0, y1);
+  for (int j = 0; j < MAXJ; ++j) {
+    const int g = lane + 32 * j;
+    if (g < ngroups) {
+      const float4 ga = __ldg(g4 + g), be = __ldg(b4 + g);
+      float4 y;
+      y.x = v[j].x * rstd * ga.x + be.x;
+      y.y = v[j].y * rstd * ga.y + be.y;
+      y.z = v[j].z * rstd * ga.z + be.z;
+      y.w = v[j].w * rstd * ga.w + be.w;
+      if (out_bf16) {
+        uint2 o;
+        o.x = pack_bf16x2(y.x, y.y);
+        o.y = pack_bf16x2(y.z, y.w);
+        reinterpret_cast<uint2*>(out_bf16 + row * D)[g] = o;
+      }
+      if (out_f32) reinterpret_cast<float4*>(out_f32 + row * D)[g] = y;
     }
+  }
 }
 
 __global__ void pad_cast_kernel(const float* __restrict__ x, int T, int d, int pad, __nv_bfloat16* __restrict__ out,
@@ -284,7 +301,7 @@ int fe_layer0(const float* wave, long long in_stride, int B, int L, const float*
 int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
                    const float* gamma, const float* beta, void* out_bf16, float* out_f32, cudaStream_t stream) {
   OASR_REQUIRE(in && gamma && beta && (out_bf16 || out_f32), "layernorm: bad arguments");
-  OASR_REQUIRE(D % 64 == 0 && D <= 2048 && D > 0, "layernorm: D must be a multiple of 64 and <= 2048");
+  OASR_REQUIRE(D % 4 == 0 && D <= 2048 && D > 0, "layernorm: D must be a multiple of 4 and <= 2048");
   const long long total = (long long)batches * rows_per_batch;
   if (total == 0) return OASR_OK;
   const int rows_per_block = 8;

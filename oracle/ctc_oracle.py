@@ -54,6 +54,7 @@ import torch.nn.functional as F
 SAMPLE_RATE = 16_000
 LN_EPS = 1e-5
 BLANK_ID = 0
+LOG2E = 1.4426950408889634
 # (out_channels, kernel, stride) of the 7 feature-extractor layers (a9-a11).
 FE_LAYERS: Tuple[Tuple[int, int, int], ...] = (
     (512, 10, 5), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 3, 2), (512, 2, 2), (512, 2, 2))
@@ -305,10 +306,13 @@ def forward(w: Dict[str, torch.Tensor], wave: torch.Tensor, n_samples: Sequence[
         vh = vh.view(B, T, H, hd).transpose(1, 2)
         s = torch.matmul(qh, kh.transpose(-1, -2)) * scale + key_bias
         if q:
-            # engine: p = bf16(exp(s - rowmax)) feeds P.V; row sum taken over fp32 p
-            m = s.amax(dim=-1, keepdim=True)
+            # engine (attention_v2.cu): P = bf16(2^(s*c - m_ref)) feeds P.V, with c = scale*log2(e) and an
+            # INTEGER reference m_ref = ceil(rowmax * c) (any integer gives the same bf16 mantissas); the row
+            # sum is taken over the unrounded fp32 P.
+            sl = s * LOG2E
+            m = torch.ceil(sl.amax(dim=-1, keepdim=True))
             m = torch.where(torch.isinf(m), torch.zeros_like(m), m)
-            pr = torch.exp(s - m)
+            pr = torch.exp2(sl - m)
             den = pr.sum(dim=-1, keepdim=True)
             a = torch.matmul(_q(pr, True), vh) / den
         else:

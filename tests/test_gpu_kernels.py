@@ -163,7 +163,7 @@ def test_wave_norm(device, gen):
     assert (out[1, 31337:] == 0).all() and (out[3] == 0).all()
 
 
-@pytest.mark.parametrize("D,bf16_in", [(512, True), (1280, False), (2048, False), (256, False)])
+@pytest.mark.parametrize("D,bf16_in", [(512, True), (1280, False), (2048, False), (256, False), (320, False)])
 def test_layernorm(device, gen, D, bf16_in):
     rows = 1001
     x = _rand((rows, D), gen, 2.0) + 0.5
@@ -222,8 +222,9 @@ def test_attention(device, gen, H, hd, T, B, ragged):
     s = q @ k.transpose(-1, -2) * scale
     mask = torch.arange(T, device=device)[None, :] >= nfd[:, None]
     s = s.masked_fill(mask[:, None, None, :], float("-inf"))
-    m = s.amax(-1, keepdim=True)
-    p = torch.exp(s - m)
+    sl = s * 1.4426950408889634
+    m = torch.ceil(sl.amax(-1, keepdim=True))                # integer reference in the log2 domain
+    p = torch.exp2(sl - m)
     ref = (bf16_round(p) @ v) / p.sum(-1, keepdim=True)      # the engine's numerics contract
     ref = ref.permute(0, 2, 1, 3).reshape(B * T, d)
     o = out.float().view(B, T, d)
@@ -234,6 +235,31 @@ def test_attention(device, gen, H, hd, T, B, ragged):
     # and against the textbook softmax (P not rounded): bf16-level agreement
     ref2 = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, T, d)
     assert rel_err(o[0], ref2[0]) < 1e-2
+
+
+def test_attention_growing_scores_take_the_rescale_path(device, gen):
+    """Keys whose scores grow along the sequence push the running reference up by > 2^8 several times."""
+    H, hd, T, B = 2, 64, 700, 1
+    d = H * hd
+    qkv = _rand((B * T, 3 * d), gen, 0.5)
+    ramp = torch.linspace(0.0, 6.0, T, device=device)
+    qkv[:, :d] = 1.0 + 0.1 * qkv[:, :d]                       # q ~ all ones
+    qkv[:, d:2 * d] = ramp[:, None] + 0.1 * qkv[:, d:2 * d]   # k grows with the position
+    qkv = qkv.bfloat16()
+    out = torch.zeros((B * T, d), dtype=torch.bfloat16, device=device)
+    nfd = torch.tensor([T], dtype=torch.int32, device=device)
+    scale = hd ** -0.5
+    N.check(lib().oasr_attention(N.ptr(qkv), N.ptr(out), N.ptr(nfd), B, T, H, hd, scale, N.stream_ptr()), "attention")
+    sync()
+    q, k, v = qkv.float().view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) * scale
+    assert float(s.amax() - s[..., :128].amax()) * 1.4427 > 20      # the reference really has to move
+    sl = s * 1.4426950408889634
+    m = torch.ceil(sl.amax(-1, keepdim=True))
+    p = torch.exp2(sl - m)
+    ref = ((bf16_round(p) @ v) / p.sum(-1, keepdim=True)).permute(0, 2, 1, 3).reshape(B * T, d)
+    assert torch.allclose(out.float(), ref, rtol=1e-2, atol=1e-2)
+    assert rel_err(out, ref) < 5e-3
 
 
 def test_attention_fully_padded_window_is_zero(device, gen):
