@@ -1,7 +1,9 @@
 // Bidirectional self-attention on tcgen05, second version (a14): one (sequence, head, 128-query tile) per CTA,
 // ONE pass over the keys, everything between the two MMAs stays in tensor memory.
 //
-//   S_j = Q K_j^T             tcgen05.mma SS, both operands K-major bf16 in 32B-swizzled 16-column chunks;
+//   S_j = Q K_j^T             tcgen05.mma SS, both operands K-major bf16; the head dimension is cut into column
+//                             chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle) so any head_dim % 16 == 0 works
+//                             with the widest possible TMA boxes (80 = 64 + 16);
 //                             S is double buffered in TMEM so S_{j+1} runs under the softmax of block j
 //   P_j = 2^(S_j c - m_ref)   one softmax thread per query row (= TMEM lane); m_ref is an INTEGER in the log2
 //                             domain, so a change of reference rescales P, the row sum and O by an exact power
@@ -28,14 +30,24 @@ namespace {
 constexpr int ATT_THREADS = 192;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int CH = 16;                  // head-dim columns per smem chunk (32 bytes, SWIZZLE_32B)
-constexpr int CH_BYTES = 128 * CH * 2;  // one [128 rows][16 cols] chunk
-constexpr int KV_STAGES = 2;
+constexpr int MAX_CHUNKS = 3;  // head_dim is cut into column chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle)
+constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S = 0, TM_O = 256, TM_P = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8 relative to the reference
 
+// One column chunk of a Q / K / V tile: [128 rows][w cols] bf16, rows of 2w bytes, swizzle = row size.
+struct Chunk {
+  int col;      // first head-dim column
+  int w;        // 64, 32 or 16 columns
+  int off;      // byte offset inside the tile
+  int map;      // which tensor map (0: 64-col boxes, 1: 32-col, 2: 16-col)
+  uint32_t swz; // UMMA layout type
+};
+
 struct AttnParams {
+  Chunk ch[MAX_CHUNKS];
+  int nch, tile_bytes, kv_stages;
   int T, H, hd, d;
   float scale_log2e;
   const int* n_frames;
@@ -49,23 +61,25 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) {
+attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32,
+                    const __grid_constant__ CUtensorMap tm16, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int nch = p.hd / CH;
-  const int tile_bytes = nch * CH_BYTES;
+  const int nch = p.nch;
+  const int tile_bytes = p.tile_bytes;
+  const int KS = p.kv_stages;
   uint8_t* sQ = smem;
   uint8_t* sKV = sQ + tile_bytes;  // [stage][K | V]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KV_STAGES * 2 * tile_bytes);
-  uint64_t* q_full = bars;          // 1
-  uint64_t* kv_full = bars + 1;     // 2
-  uint64_t* kv_empty = bars + 3;    // 2
-  uint64_t* s_full = bars + 5;      // 2
-  uint64_t* s_empty = bars + 7;     // 2
-  uint64_t* p_full = bars + 9;      // 2
-  uint64_t* p_free = bars + 11;     // 2: P.V that read P[b] has retired
-  uint64_t* o_full = bars + 13;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KS * 2 * tile_bytes);
+  uint64_t* q_full = bars;                      // 1
+  uint64_t* kv_full = bars + 1;                 // MAX_KV_STAGES
+  uint64_t* kv_empty = kv_full + MAX_KV_STAGES; // MAX_KV_STAGES
+  uint64_t* s_full = kv_empty + MAX_KV_STAGES;  // 2
+  uint64_t* s_empty = s_full + 2;               // 2
+  uint64_t* p_full = s_empty + 2;               // 2
+  uint64_t* p_free = p_full + 2;                // 2: P.V that read P[b] has retired
+  uint64_t* o_full = p_free + 2;                // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ;
@@ -84,11 +98,15 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) 
   }
 
   if (warp == 4 && lane == 0) {
-    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tm64);
+    tma_prefetch_desc(&tm32);
+    tma_prefetch_desc(&tm16);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < MAX_KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);
@@ -110,52 +128,82 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm, const AttnParams p) 
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       const int qcol = h * p.hd, kcol = p.d + h * p.hd, vcol = 2 * p.d + h * p.hd;
+      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
+        for (int c = 0; c < nch; ++c) {
+          const Chunk& k = p.ch[c];
+          const CUtensorMap* m = k.map == 0 ? &tm64 : (k.map == 1 ? &tm32 : &tm16);
+          tma_load_3d(dst + k.off, m, bar, col + k.col, row, b);
+        }
+      };
       mbar_arrive_expect_tx(q_full, tile_bytes);
-      for (int c = 0; c < nch; ++c) tma_load_3d(sQ + c * CH_BYTES, &tm, q_full, qcol + c * CH, q0, b);
+      load_tile(sQ, q_full, qcol, q0);
+      int s = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
-        const int s = j & 1;
-        mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_wait(&kv_empty[s], ph ^ 1);
         uint8_t* sK = sKV + s * 2 * tile_bytes;
-        uint8_t* sV = sK + tile_bytes;
         mbar_arrive_expect_tx(&kv_full[s], 2 * tile_bytes);
-        for (int c = 0; c < nch; ++c) tma_load_3d(sK + c * CH_BYTES, &tm, &kv_full[s], kcol + c * CH, j * BKV, b);
-        for (int c = 0; c < nch; ++c) tma_load_3d(sV + c * CH_BYTES, &tm, &kv_full[s], vcol + c * CH, j * BKV, b);
+        load_tile(sK, &kv_full[s], kcol, j * BKV);
+        load_tile(sK + tile_bytes, &kv_full[s], vcol, j * BKV);
+        if (++s == KS) {
+          s = 0;
+          ph ^= 1;
+        }
       }
     }
   } else if (warp == 5) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
-      const uint32_t idesc_o = make_idesc_bf16(BQ, p.hd, 0, 1);  // A = P from TMEM (K-major), B = V MN-major
       const uint32_t q_addr = smem_u32(sQ);
       mbar_wait(q_full, 0);
+      int ks_s = 0;      // kv stage / phase as seen by the S MMAs (run one block ahead)
+      uint32_t kph_s = 0;
       auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
-        mbar_wait(&s_empty[s], ((j >> 1) & 1) ^ 1);
+        const int sb = j & 1;
+        mbar_wait(&kv_full[ks_s], kph_s);
+        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + s * 2 * tile_bytes);
+        const uint32_t k_addr = smem_u32(sKV + ks_s * 2 * tile_bytes);
+        uint32_t acc = 0;
         for (int c = 0; c < nch; ++c) {
-          const uint64_t adesc = make_smem_desc(q_addr + c * CH_BYTES, 16, 256, SWZ_32B);
-          const uint64_t bdesc = make_smem_desc(k_addr + c * CH_BYTES, 16, 256, SWZ_32B);
-          umma_ss(tmem_base + TM_S + s * BKV, adesc, bdesc, idesc_s, c != 0 ? 1u : 0u);
+          const Chunk& k = p.ch[c];
+          for (int kk = 0; kk < k.w / 16; ++kk) {  // K-major: rows of 2w bytes, 8-row groups of 16w bytes
+            const uint64_t adesc = make_smem_desc(q_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
+            const uint64_t bdesc = make_smem_desc(k_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
+            umma_ss(tmem_base + TM_S + sb * BKV, adesc, bdesc, idesc_s, acc);
+            acc = 1;
+          }
         }
-        umma_commit(&s_full[s]);
+        umma_commit(&s_full[sb]);
+        if (++ks_s == KS) {
+          ks_s = 0;
+          kph_s ^= 1;
+        }
       };
       issue_s(0);
+      int ks = 0;  // kv stage of block j (P.V side)
       for (int j = 0; j < nblk; ++j) {
         if (j + 1 < nblk) issue_s(j + 1);
-        const int s = j & 1;
-        mbar_wait(&p_full[s], (j >> 1) & 1);
+        const int sb = j & 1;
+        mbar_wait(&p_full[sb], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + s * 2 * tile_bytes + tile_bytes);
+        const uint32_t v_addr = smem_u32(sKV + ks * 2 * tile_bytes + tile_bytes);
+        for (int c = 0; c < nch; ++c) {
+          // one MMA chain per column chunk: O[:, col .. col+w) += P . V[:, col .. col+w); V is MN-major with
+          // kv rows of 2w bytes (one swizzle atom wide), 8-row groups of 16w bytes, 16 rows per k-step
+          const Chunk& k = p.ch[c];
+          const uint32_t idesc_o = make_idesc_bf16(BQ, k.w, 0, 1);
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t bdesc = make_smem_desc(v_addr + k * (16 * CH * 2), CH_BYTES, 256, SWZ_32B);
-          umma_ts(tmem_base + TM_O, tmem_base + TM_P + s * (BKV / 2) + k * 8, bdesc, idesc_o, (j | k) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BKV / 16; ++kk) {
+            const uint64_t bdesc = make_smem_desc(v_addr + k.off + kk * (32 * k.w), 16 * k.w, 16 * k.w, k.swz);
+            umma_ts(tmem_base + TM_O + k.col, tmem_base + TM_P + sb * (BKV / 2) + kk * 8, bdesc, idesc_o,
+                    (j | kk) != 0 ? 1u : 0u);
+          }
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(&p_free[s]);
+        umma_commit(&kv_empty[ks]);
+        umma_commit(&p_free[sb]);
+        if (++ks == KS) ks = 0;
       }
       umma_commit(o_full);
     }
@@ -296,7 +344,10 @@ struct AttKey {
     return d3 < o.d3;
   }
 };
-std::map<AttKey, CUtensorMap> g_att_tmaps;
+struct AttMaps {
+  CUtensorMap tm[3];
+};
+std::map<AttKey, AttMaps> g_att_tmaps;
 std::mutex g_att_mu;
 
 }  // namespace
@@ -308,7 +359,7 @@ int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, in
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "attention: buffers must be 16-byte aligned");
   const int d = H * hd;
-  CUtensorMap tm;
+  CUtensorMap tms[3];
   {
     std::lock_guard<std::mutex> g(g_att_mu);
     AttKey key{qkv, B, T, 3 * d};
@@ -316,22 +367,47 @@ int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, in
     if (it == g_att_tmaps.end()) {
       uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
       uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
-      uint32_t box[3] = {CH, 128, 1};
-      OASR_TRY(make_tmap_bf16(&tm, qkv, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_32B));
+      AttMaps m;
+      const uint32_t widths[3] = {64, 32, 16};
+      const CUtensorMapSwizzle swz[3] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_32B};
+      for (int i = 0; i < 3; ++i) {
+        uint32_t box[3] = {widths[i], 128, 1};
+        OASR_TRY(make_tmap_bf16(&m.tm[i], qkv, 3, dims, strides, box, swz[i]));
+      }
       if (g_att_tmaps.size() > 1024) g_att_tmaps.clear();
-      g_att_tmaps[key] = tm;
+      g_att_tmaps[key] = m;
+      for (int i = 0; i < 3; ++i) tms[i] = m.tm[i];
     } else {
-      tm = it->second;
+      for (int i = 0; i < 3; ++i) tms[i] = it->second.tm[i];
     }
   }
-  const int tile_bytes = (hd / CH) * CH_BYTES;
-  const int smem_bytes = tile_bytes * (1 + 2 * KV_STAGES) + 256 + 1024;
+  AttnParams p;
+  {
+    int col = 0, off = 0, n = 0;
+    const int widths[3] = {64, 32, 16};
+    const uint32_t swz[3] = {SWZ_128B, SWZ_64B, SWZ_32B};
+    for (int i = 0; i < 3; ++i)
+      while (hd - col >= widths[i]) {
+        OASR_REQUIRE(n < MAX_CHUNKS, "attention: head_dim needs more than 3 column chunks");
+        p.ch[n++] = Chunk{col, widths[i], off, i, swz[i]};
+        col += widths[i];
+        off += 128 * widths[i] * 2;
+      }
+    for (int i = n; i < MAX_CHUNKS; ++i) p.ch[i] = Chunk{0, 0, 0, 2, SWZ_32B};
+    p.nch = n;
+    p.tile_bytes = off;
+  }
+  const int tile_bytes = p.tile_bytes;
+  int kv_stages = (227 * 1024 - 2048 - tile_bytes) / (2 * tile_bytes);
+  kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
+  OASR_REQUIRE(kv_stages >= 2, "attention: tile does not fit shared memory");
+  p.kv_stages = kv_stages;
+  const int smem_bytes = tile_bytes * (1 + 2 * kv_stages) + 256 + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
     OASR_CUDA_CHECK(cudaFuncSetAttribute(attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_smem = smem_bytes;
   }
-  AttnParams p;
   p.T = T;
   p.H = H;
   p.hd = hd;
@@ -340,7 +416,7 @@ int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   dim3 grid((T + BQ - 1) / BQ, H, B);
-  attention_v2_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tm, p);
+  attention_v2_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], p);
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }

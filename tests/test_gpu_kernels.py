@@ -305,3 +305,62 @@ def test_ctc_collapse_kats_and_random(device):
     assert (ol.cpu().numpy() == want_len).all()
     assert (oi.cpu().numpy() == want_ids).all()
     assert (of.cpu().numpy() == want_pos).all()
+
+
+# ------------------------------------------------------------------------------------------- exactness
+def test_outputs_bit_identical_to_rounded_reference(device, gen):
+    """Each bf16-producing kernel must equal 'fp64 reference rounded once to bf16' on >= 99.5 % of its outputs
+    (the remainder are fp32 summation-order flips of a rounding boundary); fp32 outputs agree to ~1e-6."""
+    def same(out, ref64):
+        return float((out.float() == ref64.float().bfloat16().float()).float().mean())
+
+    # FE layer 0 (fp32 CUDA-core conv + LN + GELU)
+    B, L = 2, 16000
+    wave = _rand((B, L), gen)
+    w = _rand((512, 1, 10), gen, 0.4)
+    bias, g, b = _rand((512,), gen, 0.3), 1 + _rand((512,), gen, 0.1), _rand((512,), gen, 0.1)
+    T0 = (L - 10) // 5 + 1
+    out = torch.zeros((B, T0, 512), dtype=torch.bfloat16, device=device)
+    N.check(lib().oasr_fe_layer0(N.ptr(wave), B, L, N.ptr(w[:, 0, :].t().contiguous()), N.ptr(bias), N.ptr(g), N.ptr(b),
+                                 N.ptr(out), N.stream_ptr()), "fe0")
+    sync()
+    ref = F.gelu(F.layer_norm(F.conv1d(wave[:, None].double(), w.double(), bias.double(), stride=5).transpose(1, 2),
+                              (512,), g.double(), b.double(), 1e-5))
+    assert same(out, ref) > 0.995
+
+    # tcgen05 GEMM with fused epilogues
+    M, Nn, K = 1000, 1280, 1280
+    A = _rand((M, K), gen).bfloat16()
+    W = _rand((Nn, K), gen, 1 / math.sqrt(K)).bfloat16()
+    bv = _rand((Nn,), gen)
+    acc = A.double() @ W.double().t() + bv.double()
+    for epi, fn in ((N.EPI_BF16, lambda t: t), (N.EPI_BF16_GELU, F.gelu)):
+        o = torch.zeros((M, Nn), dtype=torch.bfloat16, device=device)
+        gemm(A, W, bv, epi, o)
+        assert same(o, fn(acc)) > 0.995
+    o = torch.zeros((M, Nn), dtype=torch.float32, device=device)
+    gemm(A, W, bv, N.EPI_F32, o)
+    assert rel_err(o, acc.float()) < 5e-6
+
+    # implicit-GEMM conv with the LayerNorm+GELU epilogue
+    A5 = _rand((M, 1536), gen).bfloat16()
+    W5 = _rand((512, 1536), gen, 1 / math.sqrt(1536)).bfloat16()
+    o = torch.zeros((M, 512), dtype=torch.bfloat16, device=device)
+    gemm(A5, W5, bias, N.EPI_LN_GELU_BF16, o, ln_g=g, ln_b=b)
+    ref = F.gelu(F.layer_norm(A5.double() @ W5.double().t() + bias.double(), (512,), g.double(), b.double(), 1e-5))
+    assert same(o, ref) > 0.995
+
+    # attention (single pass, integer log2 reference)
+    for H, hd in ((4, 64), (4, 80), (2, 128)):
+        T, Bq = 300, 2
+        d = H * hd
+        qkv = _rand((Bq * T, 3 * d), gen).bfloat16()
+        nf = torch.full((Bq,), T, dtype=torch.int32, device=device)
+        o = torch.zeros((Bq * T, d), dtype=torch.bfloat16, device=device)
+        N.check(lib().oasr_attention(N.ptr(qkv), N.ptr(o), N.ptr(nf), Bq, T, H, hd, hd ** -0.5, N.stream_ptr()), "attn")
+        sync()
+        q, k, v = qkv.double().view(Bq, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+        sl = (q @ k.transpose(-1, -2)) * (hd ** -0.5) * 1.4426950408889634
+        p = torch.exp2(sl - torch.ceil(sl.amax(-1, keepdim=True)))
+        ref = ((p.float().bfloat16().double() @ v) / p.sum(-1, keepdim=True)).permute(0, 2, 1, 3).reshape(Bq * T, d)
+        assert same(o, ref) > 0.995
