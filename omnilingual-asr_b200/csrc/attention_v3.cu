@@ -1,5 +1,8 @@
-// Bidirectional self-attention on tcgen05, second version (a14): one (sequence, head, 128-query tile) per CTA,
-// ONE pass over the keys, everything between the two MMAs stays in tensor memory.
+// Bidirectional self-attention on tcgen05, third version (a14): one (sequence, head, PAIR of 128-query tiles) per
+// CTA, ONE pass over the keys, everything between the two MMAs stays in tensor memory.  Two softmax warpgroups
+// (one per query tile) ping-pong against a single MMA-issuing thread, so every SM sub-partition always has a
+// second warp to issue while the first waits on TMEM, MUFU or an mbarrier, and K/V tiles are fetched once per
+// 256 queries.
 //
 //   S_j = Q K_j^T             tcgen05.mma SS, both operands K-major bf16; the head dimension is cut into column
 //                             chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle) so any head_dim % 16 == 0 works
@@ -9,13 +12,15 @@
 //                             domain, so a change of reference rescales P, the row sum and O by an exact power
 //                             of two: the result is bit-identical to a two-pass softmax whose reference is
 //                             ceil(rowmax * c) - the numerics contract the oracle's emulate_bf16 mode restates
-//   O  += P_j V_j             tcgen05.mma TS: A = bf16(P_j) read from TMEM (written with tcgen05.st, double
-//                             buffered), B = V tile as an MN-major smem operand
+//   O  += P_j V_j             tcgen05.mma TS: A = bf16(P_j) read from TMEM (tcgen05.st over the first 64 columns of
+//                             the S it was computed from), B = V tile as an MN-major smem operand; MMAs of one
+//                             thread retire in order, so S_{j+1} may overwrite P_j without a barrier
 // The reference only moves when a row's scores exceed it by more than 2^8 (rare after the first block); then
-// the thread rescales its O row in TMEM and redoes the block.
+// the thread rescales its O row in TMEM and redoes the block (S is still intact: P is written last).
 //
-// TMEM columns: S0 [0,128) S1 [128,256) O [256,384) P0 [384,448) P1 [448,512).
-// Warps: 0-3 softmax + epilogue (warp w owns TMEM lanes [32w, 32w+32)), 4 TMA producer, 5 MMA issuer / TMEM.
+// TMEM columns: S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_X aliases S_X[0,64).
+// Warps: 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w owns TMEM lanes [32(w%4), +32)), 8 TMA producer,
+// 9 MMA issuer / TMEM allocator.
 #include "host_util.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -27,13 +32,13 @@
 namespace oasr {
 namespace {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int MAX_CHUNKS = 3;  // head_dim is cut into column chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle)
 constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
-constexpr int TM_S = 0, TM_O = 256, TM_P = 384;
+constexpr int TM_S = 0, TM_O = 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8 relative to the reference
 
 // One column chunk of a Q / K / V tile: [128 rows][w cols] bf16, rows of 2w bytes, swizzle = row size.
@@ -60,36 +65,69 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+
+// One pass over the 128 scores of a row: x = s*c - m_ref, P = 2^x packed to bf16 (kept in registers), partial sum
+// and maximum.  Fully unrolled so that pk[] stays in registers.
+template <bool MASKED>
+__device__ __forceinline__ void softmax_block(uint32_t t_s, float c, float m_ref, int ncols, uint32_t (&pk)[64],
+                                              float& bsum, float& bmax) {
+  bsum = 0.f;
+  bmax = -INFINITY;
+#pragma unroll
+  for (int cc = 0; cc < BKV; cc += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_s + cc, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
+      const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
+      float p0, p1;
+      if (MASKED) {
+        const bool ok0 = cc + i < ncols, ok1 = cc + i + 1 < ncols;
+        if (ok0) bmax = fmaxf(bmax, x0);
+        if (ok1) bmax = fmaxf(bmax, x1);
+        p0 = ok0 ? ex2(x0) : 0.f;
+        p1 = ok1 ? ex2(x1) : 0.f;
+      } else {
+        bmax = fmaxf(bmax, fmaxf(x0, x1));
+        p0 = ex2(x0);
+        p1 = ex2(x1);
+      }
+      bsum += p0 + p1;
+      pk[(cc + i) >> 1] = pack_bf16x2(p0, p1);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32,
+attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32,
                     const __grid_constant__ CUtensorMap tm16, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int nch = p.nch;
   const int tile_bytes = p.tile_bytes;
   const int KS = p.kv_stages;
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + tile_bytes;  // [stage][K | V]
+  uint8_t* sQ = smem;                  // [2 tiles]
+  uint8_t* sKV = sQ + 2 * tile_bytes;  // [stage][K | V]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KS * 2 * tile_bytes);
-  uint64_t* q_full = bars;                      // 1
-  uint64_t* kv_full = bars + 1;                 // MAX_KV_STAGES
-  uint64_t* kv_empty = kv_full + MAX_KV_STAGES; // MAX_KV_STAGES
-  uint64_t* s_full = kv_empty + MAX_KV_STAGES;  // 2
-  uint64_t* s_empty = s_full + 2;               // 2
-  uint64_t* p_full = s_empty + 2;               // 2
-  uint64_t* p_free = p_full + 2;                // 2: P.V that read P[b] has retired
-  uint64_t* o_full = p_free + 2;                // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* kv_full = bars + 1;                  // MAX_KV_STAGES
+  uint64_t* kv_empty = kv_full + MAX_KV_STAGES;  // MAX_KV_STAGES
+  uint64_t* s_full = kv_empty + MAX_KV_STAGES;   // 2 (per query tile)
+  uint64_t* p_full = s_full + 2;                 // 2
+  uint64_t* o_done = p_full + 2;                 // 2: P.V_X(j) has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
+  const int q0 = blockIdx.x * (2 * BQ);
   const int h = blockIdx.y;
   const int b = blockIdx.z;
   const int n_keys = min(p.n_frames ? p.n_frames[b] : p.T, p.T);
   const int nblk = (n_keys + BKV - 1) / BKV;
 
   if (nblk == 0) {  // fully padded window: attention output is defined as zero
-    for (int i = threadIdx.x; i < BQ * (p.hd / 8); i += blockDim.x) {
+    for (int i = threadIdx.x; i < 2 * BQ * (p.hd / 8); i += blockDim.x) {
       const int r = i / (p.hd / 8), c8 = i % (p.hd / 8);
       if (q0 + r < p.T)
         reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * p.d + h * p.hd)[c8] = make_uint4(0, 0, 0, 0);
@@ -97,7 +135,7 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
     return;
   }
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm64);
     tma_prefetch_desc(&tm32);
     tma_prefetch_desc(&tm16);
@@ -108,14 +146,12 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
       mbar_init(&p_full[i], 4);
-      mbar_init(&p_free[i], 1);
+      mbar_init(&o_done[i], 1);
     }
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -124,7 +160,7 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       const int qcol = h * p.hd, kcol = p.d + h * p.hd, vcol = 2 * p.d + h * p.hd;
@@ -135,8 +171,9 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
           tma_load_3d(dst + k.off, m, bar, col + k.col, row, b);
         }
       };
-      mbar_arrive_expect_tx(q_full, tile_bytes);
+      mbar_arrive_expect_tx(q_full, 2 * tile_bytes);
       load_tile(sQ, q_full, qcol, q0);
+      load_tile(sQ + tile_bytes, q_full, qcol, q0 + BQ);
       int s = 0;
       uint32_t ph = 0;
       for (int j = 0; j < nblk; ++j) {
@@ -151,75 +188,85 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
-      const uint32_t q_addr = smem_u32(sQ);
       mbar_wait(q_full, 0);
-      int ks_s = 0;      // kv stage / phase as seen by the S MMAs (run one block ahead)
-      uint32_t kph_s = 0;
-      auto issue_s = [&](int j) {
-        const int sb = j & 1;
-        mbar_wait(&kv_full[ks_s], kph_s);
-        mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sKV + ks_s * 2 * tile_bytes);
+      // S_X = Q_X K^T for the K tile in stage `st`
+      auto issue_s = [&](int X, int st) {
+        const uint32_t q_addr = smem_u32(sQ + X * tile_bytes);
+        const uint32_t k_addr = smem_u32(sKV + st * 2 * tile_bytes);
         uint32_t acc = 0;
         for (int c = 0; c < nch; ++c) {
           const Chunk& k = p.ch[c];
           for (int kk = 0; kk < k.w / 16; ++kk) {  // K-major: rows of 2w bytes, 8-row groups of 16w bytes
             const uint64_t adesc = make_smem_desc(q_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
             const uint64_t bdesc = make_smem_desc(k_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
-            umma_ss(tmem_base + TM_S + sb * BKV, adesc, bdesc, idesc_s, acc);
+            umma_ss(tmem_base + TM_S + X * BKV, adesc, bdesc, idesc_s, acc);
             acc = 1;
           }
         }
-        umma_commit(&s_full[sb]);
-        if (++ks_s == KS) {
-          ks_s = 0;
-          kph_s ^= 1;
-        }
+        umma_commit(&s_full[X]);
       };
-      issue_s(0);
-      int ks = 0;  // kv stage of block j (P.V side)
-      for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) issue_s(j + 1);
-        const int sb = j & 1;
-        mbar_wait(&p_full[sb], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sKV + ks * 2 * tile_bytes + tile_bytes);
+      // O_X += P_X V for the V tile in stage `st`; P_X sits in the first 64 columns of S_X
+      auto issue_pv = [&](int X, int st, int j) {
+        const uint32_t v_addr = smem_u32(sKV + st * 2 * tile_bytes + tile_bytes);
         for (int c = 0; c < nch; ++c) {
-          // one MMA chain per column chunk: O[:, col .. col+w) += P . V[:, col .. col+w); V is MN-major with
-          // kv rows of 2w bytes (one swizzle atom wide), 8-row groups of 16w bytes, 16 rows per k-step
           const Chunk& k = p.ch[c];
-          const uint32_t idesc_o = make_idesc_bf16(BQ, k.w, 0, 1);
+          const uint32_t idesc_o = make_idesc_bf16(BQ, k.w, 0, 1);  // B = V is MN-major
 #pragma unroll
           for (int kk = 0; kk < BKV / 16; ++kk) {
             const uint64_t bdesc = make_smem_desc(v_addr + k.off + kk * (32 * k.w), 16 * k.w, 16 * k.w, k.swz);
-            umma_ts(tmem_base + TM_O + k.col, tmem_base + TM_P + sb * (BKV / 2) + kk * 8, bdesc, idesc_o,
+            umma_ts(tmem_base + TM_O + X * BQ + k.col, tmem_base + TM_S + X * BKV + kk * 8, bdesc, idesc_o,
                     (j | kk) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&kv_empty[ks]);
-        umma_commit(&p_free[sb]);
-        if (++ks == KS) ks = 0;
+        umma_commit(&o_done[X]);
+      };
+      int st = 0, st_next = KS > 1 ? 1 : 0;
+      uint32_t ph = 0, ph_next = KS > 1 ? 0 : 1;   // phase of stage st / st_next
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      for (int j = 0; j < nblk; ++j) {
+        const bool more = j + 1 < nblk;
+        for (int X = 0; X < 2; ++X) {
+          mbar_wait(&p_full[X], j & 1);
+          tc_fence_after();
+          issue_pv(X, st, j);
+          if (more) {
+            if (X == 0) {
+              mbar_wait(&kv_full[st_next], ph_next);
+              tc_fence_after();
+            }
+            issue_s(X, st_next);  // retires after P.V_X(j): same thread, in order
+          }
+        }
+        umma_commit(&kv_empty[st]);
+        st = st_next;
+        ph = ph_next;
+        if (++st_next == KS) {
+          st_next = 0;
+        }
+        ph_next = (st_next == 0) ? (ph ^ 1) : ph;
+        if (KS == 1) ph_next = ph ^ 1;
       }
-      umma_commit(o_full);
     }
   } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 0-3)
-    const int r = warp * 32 + lane;  // query row within the tile == TMEM lane
-    const uint32_t t_lane = tmem_base + (uint32_t(warp * 32) << 16);
+    // ---------------------------------------------------------------- softmax + epilogue (warps 0-7)
+    const int X = warp >> 2;                     // query tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;        // row within the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_lane + TM_S + X * BKV;
+    const uint32_t t_o = t_lane + TM_O + X * BQ;
     const float c = p.scale_log2e;
     float m_ref = 0.f;  // integer-valued reference in the log2 domain
     float sum = 0.f;
     for (int j = 0; j < nblk; ++j) {
-      const int s = j & 1;
-      const uint32_t t_s = t_lane + TM_S + s * BKV;
-      const uint32_t t_p = t_lane + TM_P + s * (BKV / 2);
       const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
-      mbar_wait(&s_full[s], (j >> 1) & 1);
+      mbar_wait(&s_full[X], j & 1);
       tc_fence_after();
       if (j == 0) {  // first block: find the reference before any P is produced
         float mx = -INFINITY;
@@ -234,44 +281,10 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         }
         m_ref = ceilf(mx * c);
       }
-      mbar_wait(&p_free[s], ((j >> 1) & 1) ^ 1);  // P.V_{j-2} no longer reads this P buffer
+      uint32_t pk[64];
       float bsum, bmax;
-      auto produce_p = [&]() {
-        bsum = 0.f;
-        bmax = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < BKV; cc += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_s + cc, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
-          if (cc + 32 <= ncols) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
-              const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
-              bmax = fmaxf(bmax, fmaxf(x0, x1));
-              const float p0 = ex2(x0), p1 = ex2(x1);
-              bsum += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
-              const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
-              const bool ok0 = cc + i < ncols, ok1 = cc + i + 1 < ncols;
-              if (ok0) bmax = fmaxf(bmax, x0);
-              if (ok1) bmax = fmaxf(bmax, x1);
-              const float p0 = ok0 ? ex2(x0) : 0.f, p1 = ok1 ? ex2(x1) : 0.f;
-              bsum += p0 + p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
-            }
-          }
-          tmem_st16(t_p + (cc >> 1), pk);
-        }
-      };
-      produce_p();
+      if (ncols == BKV) softmax_block<false>(t_s, c, m_ref, ncols, pk, bsum, bmax);
+      else softmax_block<true>(t_s, c, m_ref, ncols, pk, bsum, bmax);
       // a row whose scores outgrew the reference moves it by an integer and rescales by an exact power of two
       const bool grow = bmax > RESCALE_THRESHOLD;
       if (__any_sync(0xffffffffu, grow)) {
@@ -280,39 +293,46 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         m_ref += k;
         sum *= f;
         if (j > 0) {
-          mbar_wait(&p_free[s ^ 1], ((j - 1) >> 1) & 1);  // P.V_{j-1} has finished updating O
+          mbar_wait(&o_done[X], (j - 1) & 1);  // P.V_X(j-1) has finished updating O_X
           tc_fence_after();
 #pragma unroll 1
           for (int cc = 0; cc < p.hd; cc += 16) {
             uint32_t v[16];
-            tmem_ld16(t_lane + TM_O + cc, v);
+            tmem_ld16(t_o + cc, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-            tmem_st16(t_lane + TM_O + cc, v);
+            tmem_st16(t_o + cc, v);
           }
         }
-        produce_p();
+        if (ncols == BKV) softmax_block<false>(t_s, c, m_ref, ncols, pk, bsum, bmax);
+        else softmax_block<true>(t_s, c, m_ref, ncols, pk, bsum, bmax);
       }
       sum += bsum;
+      // P overwrites the first 64 columns of S (every score of the row has been consumed by now)
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t w16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w16[i] = pk[q4 * 16 + i];
+        tmem_st16(t_s + q4 * 16, w16);
+      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[s]);
-        mbar_arrive(&p_full[s]);
-      }
+      if (lane == 0) mbar_arrive(&p_full[X]);
     }
     // epilogue: O / rowsum -> bf16
-    mbar_wait(o_full, 0);
+    mbar_wait(&o_done[X], (nblk - 1) & 1);
     tc_fence_after();
     const float inv = 1.0f / sum;
-    const bool row_ok = (q0 + r) < p.T;
-    __nv_bfloat16* orow = p.out + ((long long)b * p.T + q0 + r) * p.d + h * p.hd;
+    const int qrow = q0 + X * BQ + r;
+    const bool row_ok = qrow < p.T;
+    __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * p.hd;
 #pragma unroll 1
     for (int cc = 0; cc < p.hd; cc += 16) {
       uint32_t v[16];
-      tmem_ld16(t_lane + TM_O + cc, v);
+      tmem_ld16(t_o + cc, v);
       tmem_ld_wait();
       if (row_ok) {
         uint32_t o[8];
@@ -328,7 +348,7 @@ attention_v2_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
   }
 
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -352,7 +372,7 @@ std::mutex g_att_mu;
 
 }  // namespace
 
-int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+int attention_bf16_v3(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream) {
   OASR_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "attention: bad arguments");
   OASR_REQUIRE(hd % 16 == 0 && hd >= 16 && hd <= 128, "attention: head_dim must be a multiple of 16 in [16, 128]");
@@ -398,14 +418,14 @@ int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, in
     p.tile_bytes = off;
   }
   const int tile_bytes = p.tile_bytes;
-  int kv_stages = (227 * 1024 - 2048 - tile_bytes) / (2 * tile_bytes);
+  int kv_stages = (227 * 1024 - 2048 - 2 * tile_bytes) / (2 * tile_bytes);
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
   OASR_REQUIRE(kv_stages >= 2, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
-  const int smem_bytes = tile_bytes * (1 + 2 * kv_stages) + 256 + 1024;
+  const int smem_bytes = tile_bytes * (2 + 2 * kv_stages) + 256 + 1024;
   static int attr_smem = 0;
   if (smem_bytes > attr_smem) {
-    OASR_CUDA_CHECK(cudaFuncSetAttribute(attention_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    OASR_CUDA_CHECK(cudaFuncSetAttribute(attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr_smem = smem_bytes;
   }
   p.T = T;
@@ -415,10 +435,21 @@ int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, in
   p.scale_log2e = scale * 1.4426950408889634f;
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
-  dim3 grid((T + BQ - 1) / BQ, H, B);
-  attention_v2_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], p);
+  dim3 grid((T + 2 * BQ - 1) / (2 * BQ), H, B);
+  attention_v3_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], p);
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
+}
+
+int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+                   cudaStream_t stream) {
+  static const int version = [] {
+    const char* e = std::getenv("OASR_ATTN");
+    return e != nullptr ? std::atoi(e) : 3;
+  }();
+  if (version == 1) return attention_bf16_v1(qkv, out, n_frames, B, T, H, hd, scale, stream);
+  if (version == 2) return attention_bf16_v2(qkv, out, n_frames, B, T, H, hd, scale, stream);
+  return attention_bf16_v3(qkv, out, n_frames, B, T, H, hd, scale, stream);
 }
 
 }  // namespace oasr
