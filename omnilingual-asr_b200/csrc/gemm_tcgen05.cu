@@ -12,6 +12,7 @@
 #include "host_util.h"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -45,10 +46,12 @@ struct GemmKernelParams {
   int frames_per_seq;
 };
 
-template <int BN>
+// CG = CTAs cooperating on one tile (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile with each
+// CTA holding 128 rows of A, half of the B rows and 128 rows of the accumulator.
+template <int BN, int CG = 1>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
@@ -63,22 +66,27 @@ struct GemmCfg {
 struct TileCoord {
   int n_tile, m0, b, g;
 };
-__device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int tile) {
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int tile, int cta_rank) {
   TileCoord t;
   t.n_tile = tile % p.n_tiles;
   int mt = tile / p.n_tiles;
-  t.m0 = (mt % p.m_tiles_per_batch) * BM;
+  t.m0 = (mt % p.m_tiles_per_batch) * (BM * CG) + cta_rank * BM;
   mt /= p.m_tiles_per_batch;
   t.b = mt % p.batches;
   t.g = mt / p.batches;
   return t;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const GemmKernelParams p) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, CG>;
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* bar_base = smem + C::STAGES * C::STAGE_BYTES;
@@ -106,16 +114,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], EPI_WARPS);
+      mbar_init(&tempty[a], EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (CG == 2) {
+      tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -124,18 +137,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+        const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sA = smem + s * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
           const int tap = kb / p.kb_per_tap;
           const int c0 = (kb - tap * p.kb_per_tap) * BK;
-          mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
-          tma_load_5d(sA, &tmA, &full[s], c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
-          for (int j = 0; j < BN && j < p.N; j += p.b_box_rows)
-            tma_load_3d(sB + j * (BK * 2), &tmB, &full[s], kb * BK, t.n_tile * BN + j, t.g);
+          if constexpr (CG == 2) {
+            // both CTAs' bytes are credited to the leader's barrier, which the leader arms for the pair
+            const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
+            if (leader) mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
+            tma_load_5d_cg2(sA, &tmA, bar, c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
+            for (int j = 0; j < BN && j < p.N; j += 256)
+              tma_load_3d_cg2(sB + (j / 2) * (BK * 2), &tmB, bar, kb * BK,
+                              t.n_tile * BN + j + cta_rank * p.b_box_rows, t.g);
+          } else {
+            mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
+            tma_load_5d(sA, &tmA, &full[s], c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
+            for (int j = 0; j < BN && j < p.N; j += p.b_box_rows)
+              tma_load_3d(sB + j * (BK * 2), &tmB, &full[s], kb * BK, t.n_tile * BN + j, t.g);
+          }
           if (++s == C::STAGES) {
             s = 0;
             ph ^= 1;
@@ -145,13 +168,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, p.umma_n, 0, 0);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_bf16(BM * CG, p.umma_n, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
       uint32_t aph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -165,17 +188,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
 #pragma unroll
             for (int j = 0; j < BN && j < p.N; j += 256) {
-              const uint64_t bdesc = make_smem_desc(b_addr + j * (BK * 2) + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
-              umma_ss(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint64_t bdesc =
+                  make_smem_desc(b_addr + (j / CG) * (BK * 2) + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
+              if constexpr (CG == 2) umma_ss_cg2(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs of a pair) when these MMAs retire
+          if constexpr (CG == 2) umma_commit_cg2(&empty[s], 3); else umma_commit(&empty[s]);
           if (++s == C::STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull[as]);  // accumulator complete
+        if constexpr (CG == 2) umma_commit_cg2(&tfull[as], 3); else umma_commit(&tfull[as]);  // accumulator complete
         if (C::ACC_STAGES == 2) {
           as ^= 1;
           if (as == 0) aph ^= 1;
@@ -191,8 +217,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int HALF_N = BN / 2;
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(p, tile);
+    const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
+      const TileCoord tc = decode_tile<CG>(p, tile, cta_rank);
       const int row_in_tile = q * 32 + lane;
       const int r = tc.m0 + row_in_tile;
       const bool row_ok = r < p.rows_per_batch;
@@ -375,7 +402,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + as * 8);
+        else mbar_arrive(&tempty[as]);
+      }
       if (C::ACC_STAGES == 2) {
         as ^= 1;
         if (as == 0) aph ^= 1;
@@ -386,10 +416,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody touches a peer's smem/TMEM past this
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -429,16 +460,16 @@ int cached_tmap(CUtensorMap* out, const TmapKey& key) {
 
 inline uint64_t nz(long long v, uint64_t fallback) { return v > 0 ? (uint64_t)v : fallback; }
 
-template <int BN, int EPI>
-int launch(const GemmArgs& a, cudaStream_t stream) {
-  using C = GemmCfg<BN>;
+template <int BN, int EPI, int CG>
+int launch_cg(const GemmArgs& a, cudaStream_t stream) {
+  using C = GemmCfg<BN, CG>;
   const int k_pad = a.k_pad > 0 ? a.k_pad : ((a.a_inner + BK - 1) / BK) * BK;
   GemmKernelParams p;
   p.rows_per_batch = a.rows_per_batch;
   p.batches = a.batches;
   p.groups = a.groups;
   p.N = a.N;
-  p.m_tiles_per_batch = (a.rows_per_batch + BM - 1) / BM;
+  p.m_tiles_per_batch = (a.rows_per_batch + BM * CG - 1) / (BM * CG);
   p.n_tiles = (a.N + BN - 1) / BN;
   p.total_tiles = p.m_tiles_per_batch * a.batches * a.groups * p.n_tiles;
   p.kb_per_tap = k_pad / BK;
@@ -446,8 +477,8 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
   p.P = a.P;
   const int n_cap = a.N < BN ? ((a.N + 15) / 16) * 16 : BN;   // columns one tile really computes
   p.umma_n = n_cap > 256 ? 256 : n_cap;
-  p.b_box_rows = p.umma_n;
-  p.stage_tx_bytes = C::A_BYTES + (uint32_t)((n_cap + p.b_box_rows - 1) / p.b_box_rows) * p.b_box_rows * BK * 2;
+  p.b_box_rows = p.umma_n / CG;   // W rows one CTA fetches per MMA-N chunk
+  p.stage_tx_bytes = (uint32_t)CG * (C::A_BYTES + (uint32_t)((n_cap + p.umma_n - 1) / p.umma_n) * p.b_box_rows * BK * 2);
   p.ldo = a.ldo;
   p.out_batch_rows = a.out_batch_rows > 0 ? a.out_batch_rows : a.rows_per_batch;
   p.out = a.out;
@@ -487,14 +518,47 @@ int launch(const GemmArgs& a, cudaStream_t stream) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    OASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
     attr_done = true;
   }
-  const int grid = p.total_tiles < device_sm_count() ? p.total_tiles : device_sm_count();
-  gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int units = device_sm_count() / CG;   // CTAs or CTA pairs that can be resident
+  const int grid_units = p.total_tiles < units ? p.total_tiles : units;
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid_units * 2);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG>, tmA, tmB, p));
+  } else {
+    gemm_kernel<BN, EPI, CG><<<grid_units, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  }
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
+}
+
+// CTA pairs whenever a tile spans full 256-column MMAs (every encoder / FE / CTC GEMM); OASR_GEMM_CG=1 forces
+// the single-CTA kernel (debugging aid).
+bool use_pairs() {
+  static const bool v = [] {
+    const char* e = std::getenv("OASR_GEMM_CG");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return v;
+}
+
+template <int BN, int EPI>
+int launch(const GemmArgs& a, cudaStream_t stream) {
+  if (BN >= 256 && a.N >= BN && use_pairs()) return launch_cg<BN, EPI, 2>(a, stream);
+  return launch_cg<BN, EPI, 1>(a, stream);
 }
 
 }  // namespace
