@@ -41,19 +41,46 @@ constexpr int TMEM_COLS = 512;
 constexpr int TM_S = 0, TM_O = 256;
 constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8 relative to the reference
 
-// One column chunk of a Q / K / V tile: [128 rows][w cols] bf16, rows of 2w bytes, swizzle = row size.
-struct Chunk {
-  int col;      // first head-dim column
-  int w;        // 64, 32 or 16 columns
-  int off;      // byte offset inside the tile
-  int map;      // which tensor map (0: 64-col boxes, 1: 32-col, 2: 16-col)
-  uint32_t swz; // UMMA layout type
-};
+// Compile-time tile layouts.  Q and K tiles ([128 rows][HD] bf16, K-major operands) are cut greedily into column
+// chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle): few TMA boxes and HD/16 MMAs per S.  V tiles (MN-major B
+// operand of P.V) use the widest chunk width that divides HD, so that ONE tcgen05.mma per 16 keys covers all HD
+// output columns (the chunks are the N-repeat of the descriptor, LBO apart): 8 MMAs per P.V instead of 8 per chunk.
+__host__ __device__ constexpr int qk_nchunks(int hd) {
+  int n = 0;
+  for (int w = 64; w >= 16; w >>= 1)
+    while (hd >= w) {
+      hd -= w;
+      ++n;
+    }
+  return n;
+}
+__host__ __device__ constexpr int qk_w(int hd, int i) {
+  int n = 0;
+  for (int w = 64; w >= 16; w >>= 1)
+    while (hd >= w) {
+      if (n == i) return w;
+      hd -= w;
+      ++n;
+    }
+  return 0;
+}
+__host__ __device__ constexpr int qk_col(int hd, int i) {
+  int c = 0;
+  for (int j = 0; j < i; ++j) c += qk_w(hd, j);
+  return c;
+}
+__host__ __device__ constexpr int v_w(int hd) { return hd % 64 == 0 ? 64 : (hd % 32 == 0 ? 32 : 16); }
+__host__ __device__ constexpr uint32_t swz_of(int w) { return w == 64 ? SWZ_128B : (w == 32 ? SWZ_64B : SWZ_32B); }
+__host__ __device__ constexpr int map_of(int w) { return w == 64 ? 0 : (w == 32 ? 1 : 2); }
+// upper 32 bits of an smem matrix descriptor: SBO, version 1, layout
+__host__ __device__ constexpr uint32_t desc_hi(int sbo_bytes, uint32_t layout) {
+  return uint32_t((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
 
 struct AttnParams {
-  Chunk ch[MAX_CHUNKS];
-  int nch, tile_bytes, kv_stages;
-  int T, H, hd, d;
+  int kv_stages;
+  int T, H, d;
   float scale_log2e;
   const int* n_frames;
   __nv_bfloat16* out;
@@ -100,13 +127,16 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, float c, float m_ref
   }
 }
 
+template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32,
                     const __grid_constant__ CUtensorMap tm16, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int nch = p.nch;
-  const int tile_bytes = p.tile_bytes;
+  constexpr int NQK = qk_nchunks(HD);
+  constexpr int VW = v_w(HD);
+  constexpr int NV = HD / VW;
+  constexpr int tile_bytes = 128 * HD * 2;
   const int KS = p.kv_stages;
   uint8_t* sQ = smem;                  // [2 tiles]
   uint8_t* sKV = sQ + 2 * tile_bytes;  // [stage][K | V]
@@ -127,10 +157,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
   const int nblk = (n_keys + BKV - 1) / BKV;
 
   if (nblk == 0) {  // fully padded window: attention output is defined as zero
-    for (int i = threadIdx.x; i < 2 * BQ * (p.hd / 8); i += blockDim.x) {
-      const int r = i / (p.hd / 8), c8 = i % (p.hd / 8);
+    for (int i = threadIdx.x; i < 2 * BQ * (HD / 8); i += blockDim.x) {
+      const int r = i / (HD / 8), c8 = i % (HD / 8);
       if (q0 + r < p.T)
-        reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * p.d + h * p.hd)[c8] = make_uint4(0, 0, 0, 0);
+        reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * p.d + h * HD)[c8] = make_uint4(0, 0, 0, 0);
     }
     return;
   }
@@ -163,13 +193,16 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
   if (warp == 8) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      const int qcol = h * p.hd, kcol = p.d + h * p.hd, vcol = 2 * p.d + h * p.hd;
-      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {
-        for (int c = 0; c < nch; ++c) {
-          const Chunk& k = p.ch[c];
-          const CUtensorMap* m = k.map == 0 ? &tm64 : (k.map == 1 ? &tm32 : &tm16);
-          tma_load_3d(dst + k.off, m, bar, col + k.col, row, b);
-        }
+      const int qcol = h * HD, kcol = p.d + h * HD, vcol = 2 * p.d + h * HD;
+      auto map = [&](int w) { return w == 64 ? &tm64 : (w == 32 ? &tm32 : &tm16); };
+      auto load_tile = [&](uint8_t* dst, uint64_t* bar, int col, int row) {   // Q / K layout
+#pragma unroll
+        for (int c = 0; c < NQK; ++c)
+          tma_load_3d(dst + 256 * qk_col(HD, c), map(qk_w(HD, c)), bar, col + qk_col(HD, c), row, b);
+      };
+      auto load_v = [&](uint8_t* dst, uint64_t* bar, int col, int row) {      // V layout: NV uniform chunks
+#pragma unroll
+        for (int c = 0; c < NV; ++c) tma_load_3d(dst + c * (256 * VW), map(VW), bar, col + c * VW, row, b);
       };
       mbar_arrive_expect_tx(q_full, 2 * tile_bytes);
       load_tile(sQ, q_full, qcol, q0);
@@ -181,7 +214,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         uint8_t* sK = sKV + s * 2 * tile_bytes;
         mbar_arrive_expect_tx(&kv_full[s], 2 * tile_bytes);
         load_tile(sK, &kv_full[s], kcol, j * BKV);
-        load_tile(sK + tile_bytes, &kv_full[s], vcol, j * BKV);
+        load_v(sK + tile_bytes, &kv_full[s], vcol, j * BKV);
         if (++s == KS) {
           s = 0;
           ph ^= 1;
@@ -190,39 +223,50 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
     }
   } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+    // The whole warp runs the (warp-uniform) control flow so that descriptor arithmetic stays in the uniform
+    // datapath; one elected lane issues the tcgen05 instructions.
+    const bool issuer = elect_one();
+    {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
       mbar_wait(q_full, 0);
-      // S_X = Q_X K^T for the K tile in stage `st`
+      const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
+      const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
+      // S_X = Q_X K^T for the K tile in stage `st`: HD/16 MMAs, descriptors differ by compile-time constants
       auto issue_s = [&](int X, int st) {
-        const uint32_t q_addr = smem_u32(sQ + X * tile_bytes);
-        const uint32_t k_addr = smem_u32(sKV + st * 2 * tile_bytes);
-        uint32_t acc = 0;
-        for (int c = 0; c < nch; ++c) {
-          const Chunk& k = p.ch[c];
-          for (int kk = 0; kk < k.w / 16; ++kk) {  // K-major: rows of 2w bytes, 8-row groups of 16w bytes
-            const uint64_t adesc = make_smem_desc(q_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
-            const uint64_t bdesc = make_smem_desc(k_addr + k.off + kk * 32, 16, 16 * k.w, k.swz);
-            umma_ss(tmem_base + TM_S + X * BKV, adesc, bdesc, idesc_s, acc);
-            acc = 1;
-          }
-        }
-        umma_commit(&s_full[X]);
-      };
-      // O_X += P_X V for the V tile in stage `st`; P_X sits in the first 64 columns of S_X
-      auto issue_pv = [&](int X, int st, int j) {
-        const uint32_t v_addr = smem_u32(sKV + st * 2 * tile_bytes + tile_bytes);
-        for (int c = 0; c < nch; ++c) {
-          const Chunk& k = p.ch[c];
-          const uint32_t idesc_o = make_idesc_bf16(BQ, k.w, 0, 1);  // B = V is MN-major
+        const uint32_t q_lo = sq_lo + X * (tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
+        const uint32_t k_lo = skv_lo + st * (2 * tile_bytes >> 4) + (1u << 16);
+        const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
+        bool first = true;
 #pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t bdesc = make_smem_desc(v_addr + k.off + kk * (32 * k.w), 16 * k.w, 16 * k.w, k.swz);
-            umma_ts(tmem_base + TM_O + X * BQ + k.col, tmem_base + TM_S + X * BKV + kk * 8, bdesc, idesc_o,
-                    (j | kk) != 0 ? 1u : 0u);
+        for (int c = 0; c < NQK; ++c) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int w = qk_w(HD, c);
+          const uint32_t hi = desc_hi(16 * w, swz_of(w));   // K-major: rows of 2w bytes, 8-row groups of 16w bytes
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < w / 16) {
+              const uint32_t off = (256 * qk_col(HD, c) + kk * 32) >> 4;
+              if (issuer) umma_ss(d_tmem, desc64(hi, q_lo + off), desc64(hi, k_lo + off), idesc_s, first ? 0u : 1u);
+              first = false;
+            }
           }
         }
-        umma_commit(&o_done[X]);
+        if (issuer) umma_commit(&s_full[X]);
+      };
+      // O_X += P_X V for the V tile in stage `st`; P_X sits in the first 64 columns of S_X.  V is MN-major: kv
+      // rows of 2*VW bytes, 8-row groups SBO = 16*VW apart, the NV column chunks LBO = 256*VW apart.
+      auto issue_pv = [&](int X, int st, int j) {
+        constexpr uint32_t hi = desc_hi(16 * VW, swz_of(VW));
+        const uint32_t v_lo = skv_lo + ((st * 2 * tile_bytes + tile_bytes) >> 4) + (uint32_t((256 * VW) >> 4) << 16);
+        const uint32_t d_tmem = tmem_base + TM_O + X * BQ;
+        const uint32_t p_tmem = tmem_base + TM_S + X * BKV;
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk)
+          if (issuer)
+            umma_ts(d_tmem, p_tmem + kk * 8, desc64(hi, v_lo + ((kk * 32 * VW) >> 4)), idesc_o, (j | kk) != 0 ? 1u : 0u);
+        if (issuer) umma_commit(&o_done[X]);
       };
       int st = 0, st_next = KS > 1 ? 1 : 0;
       uint32_t ph = 0, ph_next = KS > 1 ? 0 : 1;   // phase of stage st / st_next
@@ -244,7 +288,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
             issue_s(X, st_next);  // retires after P.V_X(j): same thread, in order
           }
         }
-        umma_commit(&kv_empty[st]);
+        if (issuer) umma_commit(&kv_empty[st]);
+        __syncwarp();
         st = st_next;
         ph = ph_next;
         if (++st_next == KS) {
@@ -296,7 +341,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
           mbar_wait(&o_done[X], (j - 1) & 1);  // P.V_X(j-1) has finished updating O_X
           tc_fence_after();
 #pragma unroll 1
-          for (int cc = 0; cc < p.hd; cc += 16) {
+          for (int cc = 0; cc < HD; cc += 16) {
             uint32_t v[16];
             tmem_ld16(t_o + cc, v);
             tmem_ld_wait();
@@ -328,9 +373,9 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
     const float inv = 1.0f / sum;
     const int qrow = q0 + X * BQ + r;
     const bool row_ok = qrow < p.T;
-    __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * p.hd;
+    __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * HD;
 #pragma unroll 1
-    for (int cc = 0; cc < p.hd; cc += 16) {
+    for (int cc = 0; cc < HD; cc += 16) {
       uint32_t v[16];
       tmem_ld16(t_o + cc, v);
       tmem_ld_wait();
@@ -402,41 +447,45 @@ int attention_bf16_v3(const void* qkv, void* out, const int* n_frames, int B, in
     }
   }
   AttnParams p;
-  {
-    int col = 0, off = 0, n = 0;
-    const int widths[3] = {64, 32, 16};
-    const uint32_t swz[3] = {SWZ_128B, SWZ_64B, SWZ_32B};
-    for (int i = 0; i < 3; ++i)
-      while (hd - col >= widths[i]) {
-        OASR_REQUIRE(n < MAX_CHUNKS, "attention: head_dim needs more than 3 column chunks");
-        p.ch[n++] = Chunk{col, widths[i], off, i, swz[i]};
-        col += widths[i];
-        off += 128 * widths[i] * 2;
-      }
-    for (int i = n; i < MAX_CHUNKS; ++i) p.ch[i] = Chunk{0, 0, 0, 2, SWZ_32B};
-    p.nch = n;
-    p.tile_bytes = off;
-  }
-  const int tile_bytes = p.tile_bytes;
+  const int tile_bytes = 128 * hd * 2;
   int kv_stages = (227 * 1024 - 2048 - 2 * tile_bytes) / (2 * tile_bytes);
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
   OASR_REQUIRE(kv_stages >= 2, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
   const int smem_bytes = tile_bytes * (2 + 2 * kv_stages) + 256 + 1024;
-  static int attr_smem = 0;
-  if (smem_bytes > attr_smem) {
-    OASR_CUDA_CHECK(cudaFuncSetAttribute(attention_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    attr_smem = smem_bytes;
-  }
   p.T = T;
   p.H = H;
-  p.hd = hd;
   p.d = d;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   dim3 grid((T + 2 * BQ - 1) / (2 * BQ), H, B);
-  attention_v3_kernel<<<grid, ATT_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], p);
+  cudaError_t attr_err = cudaSuccess;
+#define OASR_ATT_CASE(HDV)                                                                                      \
+  case HDV: {                                                                                                   \
+    static bool attr_done = false;                                                                              \
+    if (!attr_done) {                                                                                           \
+      attr_err = cudaFuncSetAttribute(attention_v3_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                      227 * 1024);                                                              \
+      attr_done = attr_err == cudaSuccess;                                                                      \
+    }                                                                                                           \
+    if (attr_err == cudaSuccess)                                                                                \
+      attention_v3_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(tms[0], tms[1], tms[2], p);           \
+    break;                                                                                                      \
+  }
+  switch (hd) {
+    OASR_ATT_CASE(16)
+    OASR_ATT_CASE(32)
+    OASR_ATT_CASE(48)
+    OASR_ATT_CASE(64)
+    OASR_ATT_CASE(80)
+    OASR_ATT_CASE(96)
+    OASR_ATT_CASE(112)
+    OASR_ATT_CASE(128)
+    default: return fail(OASR_ERR_UNSUPPORTED, "attention: head_dim must be a multiple of 16 in [16, 128]");
+  }
+#undef OASR_ATT_CASE
+  OASR_CUDA_CHECK(attr_err);
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }

@@ -168,8 +168,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && leader) {
+    // The whole warp runs the warp-uniform control flow (descriptor arithmetic stays in the uniform datapath);
+    // one elected lane of the leader CTA issues the tcgen05 instructions.
+    const bool issuer = elect_one();
+    if (leader) {
       const uint32_t idesc = make_idesc_bf16(BM * CG, p.umma_n, 0, 0);
+      constexpr uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (uint32_t(SWZ_128B) << 29);  // SBO, v1, layout
+      const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);                      // LBO field = 1
+      const bool two_chunks = BN > 256 && p.N > 256;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -181,27 +187,38 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+          const uint32_t a_lo = smem_lo + s * (C::STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc(a_addr + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
-#pragma unroll
-            for (int j = 0; j < BN && j < p.N; j += 256) {
-              const uint64_t bdesc =
-                  make_smem_desc(b_addr + (j / CG) * (BK * 2) + k * (UMMA_K * 2), 16, 1024, SWZ_128B);
-              if constexpr (CG == 2) umma_ss_cg2(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_ss(d_tmem + j, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + k * (UMMA_K * 2 >> 4));
+            const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + k * (UMMA_K * 2 >> 4));
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            if (issuer) {
+              if constexpr (CG == 2) umma_ss_cg2(d_tmem, adesc, bdesc, idesc, acc);
+              else umma_ss(d_tmem, adesc, bdesc, idesc, acc);
+            }
+            if constexpr (BN > 256) {   // second 256-column MMA of a 512-wide tile
+              const uint64_t bdesc2 = bdesc + ((256 / CG) * (BK * 2) >> 4);
+              if (issuer && two_chunks) {
+                if constexpr (CG == 2) umma_ss_cg2(d_tmem + 256, adesc, bdesc2, idesc, acc);
+                else umma_ss(d_tmem + 256, adesc, bdesc2, idesc, acc);
+              }
             }
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
-          if constexpr (CG == 2) umma_commit_cg2(&empty[s], 3); else umma_commit(&empty[s]);
+          if (issuer) {
+            if constexpr (CG == 2) umma_commit_cg2(&empty[s], 3); else umma_commit(&empty[s]);
+          }
           if (++s == C::STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        if constexpr (CG == 2) umma_commit_cg2(&tfull[as], 3); else umma_commit(&tfull[as]);  // accumulator complete
+        if (issuer) {   // accumulator complete
+          if constexpr (CG == 2) umma_commit_cg2(&tfull[as], 3); else umma_commit(&tfull[as]);
+        }
+        __syncwarp();
         if (C::ACC_STAGES == 2) {
           as ^= 1;
           if (as == 0) aph ^= 1;
