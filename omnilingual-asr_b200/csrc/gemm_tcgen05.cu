@@ -368,8 +368,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       } else {
         // fp32 outputs: EPI_F32 / EPI_F32_RESID / EPI_F32_GELU_RESID, 16 columns per transpose round
+        constexpr bool HAS_RESID = (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID);
 #pragma unroll 1
         for (int c = 0; c < HALF_N; c += 32) {
+          // The residual of the whole 32-column chunk is requested first (8 independent 16-byte loads per lane),
+          // so that its HBM latency overlaps the TMEM read and the transpose.  out may alias resid: every element
+          // is read and written by the same lane, reads of a chunk are issued before any of its writes.
+          float4 rr[2][4];
+          if constexpr (HAS_RESID) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int n = n_base + c + hh * 16 + t_piece * 4;
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int row = it * 8 + t_r8;
+                rr[hh][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rows_valid && n < p.N)
+                  rr[hh][it] = *reinterpret_cast<const float4*>(p.resid + (out_row0 + row) * p.ldo + gcol + n);
+              }
+            }
+          }
           uint32_t v[32];
           tmem_ld32(t_base + c, v);
           tmem_ld_wait();
@@ -396,9 +414,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   if constexpr (EPI == EPI_F32_GELU_RESID) {
                     a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
                   }
-                  if constexpr (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID) {
-                    const float4 rr = *reinterpret_cast<const float4*>(p.resid + grow * p.ldo + gcol + n);
-                    a.x += rr.x; a.y += rr.y; a.z += rr.z; a.w += rr.w;
+                  if constexpr (HAS_RESID) {
+                    a.x += rr[hh][it].x; a.y += rr[hh][it].y; a.z += rr[hh][it].z; a.w += rr[hh][it].w;
                   }
                   if constexpr (EPI == EPI_F32) {
                     if (p.n_valid != nullptr) {
