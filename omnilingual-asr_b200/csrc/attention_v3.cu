@@ -93,38 +93,54 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 
-// One pass over the 128 scores of a row: x = s*c - m_ref, P = 2^x packed to bf16 (kept in registers), partial sum
-// and maximum.  Fully unrolled so that pk[] stays in registers.
+// 32 scores of a row: x = s*c - m_ref, P = 2^x packed to bf16 into pk[base/2 ...], four independent partial sums
+// and two partial maxima (no serial FADD / FMNMX chain).
+template <bool MASKED>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int base, float c, float m_ref, int ncols,
+                                              uint32_t (&pk)[64], float (&sm)[4], float (&mx)[2]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
+    const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
+    float p0, p1;
+    if (MASKED) {
+      const bool ok0 = base + i < ncols, ok1 = base + i + 1 < ncols;
+      if (ok0) mx[0] = fmaxf(mx[0], x0);
+      if (ok1) mx[1] = fmaxf(mx[1], x1);
+      p0 = ok0 ? ex2(x0) : 0.f;
+      p1 = ok1 ? ex2(x1) : 0.f;
+    } else {
+      mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(x0, x1));
+      p0 = ex2(x0);
+      p1 = ex2(x1);
+    }
+    sm[(i >> 1) & 3] += p0 + p1;
+    pk[(base + i) >> 1] = pack_bf16x2(p0, p1);
+  }
+}
+
+// One pass over the 128 scores of a row (fully unrolled so that pk[] stays in registers).  The TMEM read of chunk
+// k+1 is in flight while chunk k is processed.
 template <bool MASKED>
 __device__ __forceinline__ void softmax_block(uint32_t t_s, float c, float m_ref, int ncols, uint32_t (&pk)[64],
                                               float& bsum, float& bmax) {
-  bsum = 0.f;
-  bmax = -INFINITY;
-#pragma unroll
-  for (int cc = 0; cc < BKV; cc += 32) {
-    uint32_t v[32];
-    tmem_ld32(t_s + cc, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
-      const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
-      float p0, p1;
-      if (MASKED) {
-        const bool ok0 = cc + i < ncols, ok1 = cc + i + 1 < ncols;
-        if (ok0) bmax = fmaxf(bmax, x0);
-        if (ok1) bmax = fmaxf(bmax, x1);
-        p0 = ok0 ? ex2(x0) : 0.f;
-        p1 = ok1 ? ex2(x1) : 0.f;
-      } else {
-        bmax = fmaxf(bmax, fmaxf(x0, x1));
-        p0 = ex2(x0);
-        p1 = ex2(x1);
-      }
-      bsum += p0 + p1;
-      pk[(cc + i) >> 1] = pack_bf16x2(p0, p1);
-    }
-  }
+  float sm[4] = {0.f, 0.f, 0.f, 0.f};
+  float mx[2] = {-INFINITY, -INFINITY};
+  uint32_t va[32], vb[32];
+  tmem_ld32(t_s, va);
+  tmem_ld_wait_on(va);
+  tmem_ld32(t_s + 32, vb);
+  softmax_chunk<MASKED>(va, 0, c, m_ref, ncols, pk, sm, mx);
+  tmem_ld_wait_on(vb);
+  tmem_ld32(t_s + 64, va);
+  softmax_chunk<MASKED>(vb, 32, c, m_ref, ncols, pk, sm, mx);
+  tmem_ld_wait_on(va);
+  tmem_ld32(t_s + 96, vb);
+  softmax_chunk<MASKED>(va, 64, c, m_ref, ncols, pk, sm, mx);
+  tmem_ld_wait_on(vb);
+  softmax_chunk<MASKED>(vb, 96, c, m_ref, ncols, pk, sm, mx);
+  bsum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+  bmax = fmaxf(mx[0], mx[1]);
 }
 
 template <int HD>
