@@ -15,8 +15,9 @@
 //   O  += P_j V_j             tcgen05.mma TS: A = bf16(P_j) read from TMEM (tcgen05.st over the first 64 columns of
 //                             the S it was computed from), B = V tile as an MN-major smem operand; MMAs of one
 //                             thread retire in order, so S_{j+1} may overwrite P_j without a barrier
-// The reference only moves when a row's scores exceed it by more than 2^8 (rare after the first block); then
-// the thread rescales its O row in TMEM and redoes the block (S is still intact: P is written last).
+// The reference only moves when a block's scores exceed it by ~2^80 (detected on the block sum, no per-score
+// maximum in the hot loop); then the thread rescales its O row in TMEM and redoes the block (S is still intact:
+// P is written last).
 //
 // TMEM columns: S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P_X aliases S_X[0,64).
 // Warps: 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w owns TMEM lanes [32(w%4), +32)), 8 TMA producer,
@@ -39,7 +40,7 @@ constexpr int MAX_CHUNKS = 3;  // head_dim is cut into column chunks of 64 / 32 
 constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
 constexpr int TM_S = 0, TM_O = 256;
-constexpr float RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8 relative to the reference
+constexpr float RESCALE_SUM_LIMIT = 1.2089258e24f;  // 2^80: a block sum beyond this moves the softmax reference
 
 // Compile-time tile layouts.  Q and K tiles ([128 rows][HD] bf16, K-major operands) are cut greedily into column
 // chunks of 64 / 32 / 16 (128B / 64B / 32B swizzle): few TMA boxes and HD/16 MMAs per S.  V tiles (MN-major B
@@ -84,7 +85,14 @@ struct AttnParams {
   float scale_log2e;
   const int* n_frames;
   __nv_bfloat16* out;
+  long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
 };
+constexpr int TRACE_EVENTS = 64;   // per role
+#define ATT_TRACE(role, ev)                                                                            \
+  do {                                                                                                 \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (ev) < TRACE_EVENTS) \
+      p.trace[(role) * TRACE_EVENTS + (ev)] = clock64();                                               \
+  } while (0)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -93,54 +101,60 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 
-// 32 scores of a row: x = s*c - m_ref, P = 2^x packed to bf16 into pk[base/2 ...], four independent partial sums
-// and two partial maxima (no serial FADD / FMNMX chain).
+// 32 scores of a row: x = s*c - m_ref, P = 2^x packed to bf16 into pk[base/2 ...]; packed FFMA2 / FADD2, two
+// independent pair-accumulators (no serial add chain).  Per two scores: FFMA2, 2 x MUFU.EX2, FADD2, F2FP.
 template <bool MASKED>
-__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int base, float c, float m_ref, int ncols,
-                                              uint32_t (&pk)[64], float (&sm)[4], float (&mx)[2]) {
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int base, float2 c2, float2 nm2, int ncols,
+                                              uint32_t (&pk)[64], float2 (&sm)[2]) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
-    const float x0 = fmaf(__uint_as_float(v[i]), c, -m_ref);
-    const float x1 = fmaf(__uint_as_float(v[i + 1]), c, -m_ref);
-    float p0, p1;
+    const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
+    float p0 = ex2(x.x), p1 = ex2(x.y);
     if (MASKED) {
-      const bool ok0 = base + i < ncols, ok1 = base + i + 1 < ncols;
-      if (ok0) mx[0] = fmaxf(mx[0], x0);
-      if (ok1) mx[1] = fmaxf(mx[1], x1);
-      p0 = ok0 ? ex2(x0) : 0.f;
-      p1 = ok1 ? ex2(x1) : 0.f;
-    } else {
-      mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(x0, x1));
-      p0 = ex2(x0);
-      p1 = ex2(x1);
+      if (base + i >= ncols) p0 = 0.f;
+      if (base + i + 1 >= ncols) p1 = 0.f;
     }
-    sm[(i >> 1) & 3] += p0 + p1;
+    sm[(i >> 1) & 1] = fadd2(sm[(i >> 1) & 1], make_float2(p0, p1));
     pk[(base + i) >> 1] = pack_bf16x2(p0, p1);
   }
 }
 
 // One pass over the 128 scores of a row (fully unrolled so that pk[] stays in registers).  The TMEM read of chunk
-// k+1 is in flight while chunk k is processed.
+// k+1 is in flight while chunk k is processed.  Returns the sum of the unrounded P.
 template <bool MASKED>
-__device__ __forceinline__ void softmax_block(uint32_t t_s, float c, float m_ref, int ncols, uint32_t (&pk)[64],
-                                              float& bsum, float& bmax) {
-  float sm[4] = {0.f, 0.f, 0.f, 0.f};
-  float mx[2] = {-INFINITY, -INFINITY};
+__device__ __forceinline__ float softmax_block(uint32_t t_s, float c, float m_ref, int ncols, uint32_t (&pk)[64]) {
+  const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+  float2 sm[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
   uint32_t va[32], vb[32];
   tmem_ld32(t_s, va);
   tmem_ld_wait_on(va);
   tmem_ld32(t_s + 32, vb);
-  softmax_chunk<MASKED>(va, 0, c, m_ref, ncols, pk, sm, mx);
+  softmax_chunk<MASKED>(va, 0, c2, nm2, ncols, pk, sm);
   tmem_ld_wait_on(vb);
   tmem_ld32(t_s + 64, va);
-  softmax_chunk<MASKED>(vb, 32, c, m_ref, ncols, pk, sm, mx);
+  softmax_chunk<MASKED>(vb, 32, c2, nm2, ncols, pk, sm);
   tmem_ld_wait_on(va);
   tmem_ld32(t_s + 96, vb);
-  softmax_chunk<MASKED>(va, 64, c, m_ref, ncols, pk, sm, mx);
+  softmax_chunk<MASKED>(va, 64, c2, nm2, ncols, pk, sm);
   tmem_ld_wait_on(vb);
-  softmax_chunk<MASKED>(vb, 96, c, m_ref, ncols, pk, sm, mx);
-  bsum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
-  bmax = fmaxf(mx[0], mx[1]);
+  softmax_chunk<MASKED>(vb, 96, c2, nm2, ncols, pk, sm);
+  const float2 t = fadd2(sm[0], sm[1]);
+  return t.x + t.y;
+}
+
+// Exact maximum of the valid scores of a row block (first block, and the rare reference move).
+__device__ __forceinline__ float row_block_max(uint32_t t_s, int ncols) {
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int cc = 0; cc < BKV; cc += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_s + cc, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (cc + i < ncols) mx = fmaxf(mx, __uint_as_float(v[i]));
+  }
+  return mx;
 }
 
 template <int HD>
@@ -231,6 +245,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         mbar_arrive_expect_tx(&kv_full[s], 2 * tile_bytes);
         load_tile(sK, &kv_full[s], kcol, j * BKV);
         load_v(sK + tile_bytes, &kv_full[s], vcol, j * BKV);
+        ATT_TRACE(0, j);
         if (++s == KS) {
           s = 0;
           ph ^= 1;
@@ -295,6 +310,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
         for (int X = 0; X < 2; ++X) {
           mbar_wait(&p_full[X], j & 1);
           tc_fence_after();
+          if (lane == 0) ATT_TRACE(1, j * 4 + X * 2);
           issue_pv(X, st, j);
           if (more) {
             if (X == 0) {
@@ -303,6 +319,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
             }
             issue_s(X, st_next);  // retires after P.V_X(j): same thread, in order
           }
+          if (lane == 0) ATT_TRACE(1, j * 4 + X * 2 + 1);
         }
         if (issuer) umma_commit(&kv_empty[st]);
         __syncwarp();
@@ -329,27 +346,19 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
       const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
       mbar_wait(&s_full[X], j & 1);
       tc_fence_after();
-      if (j == 0) {  // first block: find the reference before any P is produced
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int cc = 0; cc < BKV; cc += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_s + cc, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc + i < ncols) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        m_ref = ceilf(mx * c);
-      }
+      if ((warp & 3) == 0 && lane == 0) ATT_TRACE(2 + X, j * 3);
+      if (j == 0) m_ref = ceilf(row_block_max(t_s, ncols) * c);   // reference before any P is produced
       uint32_t pk[64];
-      float bsum, bmax;
-      if (ncols == BKV) softmax_block<false>(t_s, c, m_ref, ncols, pk, bsum, bmax);
-      else softmax_block<true>(t_s, c, m_ref, ncols, pk, bsum, bmax);
-      // a row whose scores outgrew the reference moves it by an integer and rescales by an exact power of two
-      const bool grow = bmax > RESCALE_THRESHOLD;
+      float bsum = ncols == BKV ? softmax_block<false>(t_s, c, m_ref, ncols, pk)
+                                : softmax_block<true>(t_s, c, m_ref, ncols, pk);
+      // P is computed against a possibly stale (too low) reference; that is exact as long as nothing overflows,
+      // because references differ by integers in the log2 domain.  A block sum beyond 2^80 (or inf) means some
+      // score outgrew the reference by more than ~80: move it to this block's maximum and rescale O and the
+      // running sum by the exact power of two.  S is still intact (P is written last), so the block is redone.
+      const bool grow = !(bsum < RESCALE_SUM_LIMIT);
       if (__any_sync(0xffffffffu, grow)) {
-        const float k = grow ? ceilf(bmax) : 0.f;
+        const float bm = row_block_max(t_s, ncols);   // warp-collective TMEM reads: every lane takes part
+        const float k = grow ? fmaxf(ceilf(fmaf(bm, c, -m_ref)), 0.f) : 0.f;
         const float f = ex2(-k);  // exact: k is an integer
         m_ref += k;
         sum *= f;
@@ -366,10 +375,11 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
             tmem_st16(t_o + cc, v);
           }
         }
-        if (ncols == BKV) softmax_block<false>(t_s, c, m_ref, ncols, pk, bsum, bmax);
-        else softmax_block<true>(t_s, c, m_ref, ncols, pk, bsum, bmax);
+        bsum = ncols == BKV ? softmax_block<false>(t_s, c, m_ref, ncols, pk)
+                            : softmax_block<true>(t_s, c, m_ref, ncols, pk);
       }
       sum += bsum;
+      if ((warp & 3) == 0 && lane == 0) ATT_TRACE(2 + X, j * 3 + 1);
       // P overwrites the first 64 columns of S (every score of the row has been consumed by now)
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -382,6 +392,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[X]);
+      if ((warp & 3) == 0 && lane == 0) ATT_TRACE(2 + X, j * 3 + 2);
     }
     // epilogue: O / rowsum -> bf16
     mbar_wait(&o_done[X], (nblk - 1) & 1);
@@ -475,6 +486,12 @@ int attention_bf16_v3(const void* qkv, void* out, const int* n_frames, int B, in
   p.scale_log2e = scale * 1.4426950408889634f;
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.trace = nullptr;
+  const char* trace_path = std::getenv("OASR_ATT_TRACE");
+  if (trace_path != nullptr) {
+    OASR_CUDA_CHECK(cudaMalloc(&p.trace, 4 * TRACE_EVENTS * sizeof(long long)));
+    OASR_CUDA_CHECK(cudaMemset(p.trace, 0, 4 * TRACE_EVENTS * sizeof(long long)));
+  }
   dim3 grid((T + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaError_t attr_err = cudaSuccess;
 #define OASR_ATT_CASE(HDV)                                                                                      \
@@ -503,6 +520,19 @@ int attention_bf16_v3(const void* qkv, void* out, const int* n_frames, int B, in
 #undef OASR_ATT_CASE
   OASR_CUDA_CHECK(attr_err);
   OASR_CUDA_CHECK(cudaGetLastError());
+  if (p.trace != nullptr) {
+    long long host[4 * TRACE_EVENTS];
+    OASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    OASR_CUDA_CHECK(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 4; ++r) {
+        for (int e = 0; e < TRACE_EVENTS; ++e) fprintf(f, "%lld ", host[r * TRACE_EVENTS + e]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return OASR_OK;
 }
 
