@@ -53,14 +53,15 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int UMMA_N = BN > 256 ? 256 : BN;
   static constexpr int BAR_BYTES = 4096;  // barriers (<256 B) + LN reduction scratch (2 KB at +256)
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 20 * 4;  // per-warp [32][20] word transpose buffers
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/;
+  static constexpr int EPI_PARAM_BYTES = 8192;  // per-warp bias slices [8][128] f32, or bias|gamma|beta [3][512] (LN)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + EPI_PARAM_BYTES + 1024 /*align slack*/;
 };
 
 struct TileCoord {
@@ -99,6 +100,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   float* red2 = red1 + 256;                                // [2][128]
   constexpr int STAGE_LD = 20;                             // words per staged row: 16 payload + 4 pad (80 B)
   uint32_t* stage = reinterpret_cast<uint32_t*>(bar_base + C::BAR_BYTES) + ((threadIdx.x >> 5) & 7) * (32 * STAGE_LD);
+  float* epi_params = reinterpret_cast<float*>(bar_base + C::BAR_BYTES + C::EPI_STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -229,9 +231,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
+    // Row-per-thread: lane l of warp w reads TMEM lane 32*(w%4) + l, so every lane of a warp works on the SAME
+    // columns and the per-column parameters (bias, gamma, beta) are warp-uniform: they are staged in shared memory
+    // and read back as broadcast 16-byte loads.  Arithmetic runs on packed fp32 pairs (FADD2 / FFMA2); the TMEM
+    // read of chunk k+1 is in flight while chunk k is processed.
     const int q = warp & 3;          // TMEM lane quarter this warp may touch
     const int half = (warp - 4) >> 2;
     constexpr int HALF_N = BN / 2;
+    constexpr bool IS_LN = EPI == EPI_LN_GELU_BF16;
+    // column parameters of this warp's half tile: [HALF_N] bias (IS_LN: + gamma + beta of the whole 512-wide row)
+    float* wbias = IS_LN ? epi_params + half * HALF_N : epi_params + (warp - 4) * 128;
+    const ulonglong2* wbias2 = reinterpret_cast<const ulonglong2*>(wbias);
+    float ln_bias_sum = 0.f;   // IS_LN: sum of the bias over this warp's columns
+    if constexpr (IS_LN) {
+      for (int i = (int)threadIdx.x - 128; i < BN; i += EPI_WARPS * 32) {
+        epi_params[i] = __ldg(p.bias + i);
+        epi_params[BN + i] = __ldg(p.ln_gamma + i);
+        epi_params[2 * BN + i] = __ldg(p.ln_beta + i);
+      }
+      named_bar_sync(5, EPI_WARPS * 32);
+      for (int i = lane; i < HALF_N; i += 32) ln_bias_sum += wbias[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ln_bias_sum += __shfl_xor_sync(0xffffffffu, ln_bias_sum, o);
+    }
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
@@ -243,11 +265,46 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long out_row = (long long)tc.b * p.out_batch_rows + r;
       const int n_base = tc.n_tile * BN + half * HALF_N;   // column within the group
       const int gcol = tc.g * p.N;                         // first output column of the group
-      const float* bias_g = p.bias ? p.bias + gcol : nullptr;
       const uint32_t t_base = tmem_base + (uint32_t(q * 32) << 16) + as * BN + half * HALF_N;
+
+      if constexpr (!IS_LN) {
+        // stage this tile's bias slice (zero beyond N); the previous tile's readers are past their __syncwarp
+        if (lane * 4 < HALF_N) {
+          const int n = n_base + lane * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && n < p.N) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gcol + n));
+          reinterpret_cast<float4*>(wbias)[lane] = b4;
+        }
+        __syncwarp();
+      }
 
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
+
+      // hands the accumulator stage back to the MMA warp; called right after the last TMEM read of the tile
+      auto release_acc = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster_relaxed(tempty_leader0 + as * 8);
+          else mbar_arrive(&tempty[as]);
+        }
+      };
+      // Software-pipelined walk over the HALF_N columns in chunks of 32: body(v, c) sees chunk c in registers.
+      auto for_each_chunk = [&](auto&& body, bool release_after_last_read) {
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_base, va);
+#pragma unroll
+        for (int c = 0; c < HALF_N; c += 64) {
+          tmem_ld_wait_on(va);
+          tmem_ld32(t_base + c + 32, vb);
+          body(va, c);
+          tmem_ld_wait_on(vb);
+          if (c + 64 < HALF_N) tmem_ld32(t_base + c + 64, va);
+          else if (release_after_last_read) release_acc();
+          body(vb, c + 32);
+        }
+      };
 
       // Rows of this warp: [m0 + 32q, +32).  Global stores (and residual loads) go through a warp-private
       // smem transpose so that one instruction covers 8 rows x 64 contiguous bytes instead of 32 rows x 16 B.
@@ -272,100 +329,97 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
       };
 
-      if constexpr (EPI == EPI_LN_GELU_BF16) {
+      if constexpr (IS_LN) {
         // LayerNorm over the 512 channels of the row: 3 passes over TMEM, partner warp holds the other half.
-        float s1 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_base + c, v);
-          tmem_ld_wait();
+        f32x2 acc0 = 0ull, acc1 = 0ull;
+        for_each_chunk([&](const uint32_t (&v)[32], int) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s1 += __uint_as_float(v[j]) + __ldg(p.bias + n_base + c + j);
-        }
-        red1[half * 128 + row_in_tile] = s1;
+          for (int j = 0; j < 32; j += 4) {
+            acc0 = f2_add(acc0, f2_pack_u(v[j], v[j + 1]));
+            acc1 = f2_add(acc1, f2_pack_u(v[j + 2], v[j + 3]));
+          }
+        }, false);
+        float sa, sb;
+        f2_unpack(f2_add(acc0, acc1), sa, sb);
+        red1[half * 128 + row_in_tile] = sa + sb + ln_bias_sum;
         named_bar_sync(1 + q, 64);
         const float mean = (red1[row_in_tile] + red1[128 + row_in_tile]) * (1.0f / BN);
-        float s2 = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_base + c, v);
-          tmem_ld_wait();
+        const f32x2 nmean2 = f2_splat(-mean);
+        acc0 = 0ull;
+        acc1 = 0ull;
+        for_each_chunk([&](const uint32_t (&v)[32], int c) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = __uint_as_float(v[j]) + __ldg(p.bias + n_base + c + j) - mean;
-            s2 += x * x;
+          for (int j = 0; j < 32; j += 4) {
+            const ulonglong2 b = wbias2[(c + j) >> 2];
+            const f32x2 d0 = f2_add(f2_add(f2_pack_u(v[j], v[j + 1]), b.x), nmean2);
+            const f32x2 d1 = f2_add(f2_add(f2_pack_u(v[j + 2], v[j + 3]), b.y), nmean2);
+            acc0 = f2_fma(d0, d0, acc0);
+            acc1 = f2_fma(d1, d1, acc1);
           }
-        }
-        red2[half * 128 + row_in_tile] = s2;
+        }, false);
+        f2_unpack(f2_add(acc0, acc1), sa, sb);
+        red2[half * 128 + row_in_tile] = sa + sb;
         named_bar_sync(1 + q, 64);
         const float var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
-        const float rstd = rsqrtf(var + 1e-5f);
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_base + c, v);
-          tmem_ld_wait();
+        const f32x2 rstd2 = f2_splat(rsqrtf(var + 1e-5f));
+        const ulonglong2* wgamma2 = reinterpret_cast<const ulonglong2*>(wbias + BN);
+        const ulonglong2* wbeta2 = reinterpret_cast<const ulonglong2*>(wbias + 2 * BN);
+        for_each_chunk([&](const uint32_t (&v)[32], int c) {
           uint32_t o[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            const int n = n_base + c + j;
-            float x0 = (__uint_as_float(v[j]) + __ldg(p.bias + n) - mean) * rstd;
-            float x1 = (__uint_as_float(v[j + 1]) + __ldg(p.bias + n + 1) - mean) * rstd;
-            x0 = gelu_erf(x0 * __ldg(p.ln_gamma + n) + __ldg(p.ln_beta + n));
-            x1 = gelu_erf(x1 * __ldg(p.ln_gamma + n + 1) + __ldg(p.ln_beta + n + 1));
-            o[j >> 1] = pack_bf16x2(x0, x1);
+          for (int j = 0; j < 32; j += 4) {
+            const ulonglong2 b = wbias2[(c + j) >> 2], g = wgamma2[(c + j) >> 2], be = wbeta2[(c + j) >> 2];
+            const f32x2 d0 = f2_add(f2_add(f2_pack_u(v[j], v[j + 1]), b.x), nmean2);
+            const f32x2 d1 = f2_add(f2_add(f2_pack_u(v[j + 2], v[j + 3]), b.y), nmean2);
+            float y0, y1, y2, y3;
+            gelu_erf_x2(f2_fma(d0, f2_mul(g.x, rstd2), be.x), y0, y1);
+            gelu_erf_x2(f2_fma(d1, f2_mul(g.y, rstd2), be.y), y2, y3);
+            o[j >> 1] = pack_bf16x2(y0, y1);
+            o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
           }
           store_bf16_chunk(o, n_base + c);
-        }
+        }, true);
       } else if constexpr (EPI == EPI_ARGMAX) {
         float best = -INFINITY;
         int best_i = 0x7fffffff;
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_base + c, v);
-          tmem_ld_wait();
+        for_each_chunk([&](const uint32_t (&v)[32], int c) {
           const int n0 = n_base + c;
-          if (n0 < p.N) {
+          if (n0 < p.N) {   // warp-uniform
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = n0 + j;
-              if (n < p.N) {
-                const float x = __uint_as_float(v[j]) + __ldg(p.bias + n);
-                if (x > best) {  // strict: lowest index wins among equals (torch.argmax)
-                  best = x;
-                  best_i = n;
-                }
+              const float x = __uint_as_float(v[j]) + wbias[c + j];
+              if (n < p.N && x > best) {  // strict: lowest index wins among equals (torch.argmax)
+                best = x;
+                best_i = n;
               }
             }
           }
-        }
+        }, true);
         if (row_ok && best_i != 0x7fffffff) atomicMax(p.argmax + out_row, argmax_pack(best, best_i));
       } else if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_GELU) {
-#pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(t_base + c, v);
-          tmem_ld_wait();
-          const int n0 = n_base + c;
-          if (n0 < p.N) {   // warp-uniform
+        for_each_chunk([&](const uint32_t (&v)[32], int c) {
+          if (n_base + c < p.N) {   // warp-uniform; columns >= N of a partial chunk are computed but not stored
             uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              // columns >= N of a partial chunk hold zero accumulators; clamp the bias index, results are not stored
-              float x0 = __uint_as_float(v[j]) + (bias_g ? __ldg(bias_g + min(n0 + j, p.N - 1)) : 0.f);
-              float x1 = __uint_as_float(v[j + 1]) + (bias_g ? __ldg(bias_g + min(n0 + j + 1, p.N - 1)) : 0.f);
+            for (int j = 0; j < 32; j += 4) {
+              const ulonglong2 b = wbias2[(c + j) >> 2];
+              const f32x2 x01 = f2_add(f2_pack_u(v[j], v[j + 1]), b.x);
+              const f32x2 x23 = f2_add(f2_pack_u(v[j + 2], v[j + 3]), b.y);
+              float y0, y1, y2, y3;
               if constexpr (EPI == EPI_BF16_GELU) {
-                x0 = gelu_erf(x0);
-                x1 = gelu_erf(x1);
+                gelu_erf_x2(x01, y0, y1);
+                gelu_erf_x2(x23, y2, y3);
+              } else {
+                f2_unpack(x01, y0, y1);
+                f2_unpack(x23, y2, y3);
               }
-              o[j >> 1] = pack_bf16x2(x0, x1);
+              o[j >> 1] = pack_bf16x2(y0, y1);
+              o[(j >> 1) + 1] = pack_bf16x2(y2, y3);
             }
-            store_bf16_chunk(o, n0);
+            store_bf16_chunk(o, n_base + c);
           }
-        }
+        }, true);
       } else {
         // fp32 outputs: EPI_F32 / EPI_F32_RESID / EPI_F32_GELU_RESID, 16 columns per transpose round
         constexpr bool HAS_RESID = (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID);
@@ -391,6 +445,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t v[32];
           tmem_ld32(t_base + c, v);
           tmem_ld_wait();
+          if (c + 32 >= HALF_N) release_acc();
           if (n_base + c < p.N) {   // warp-uniform
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
@@ -402,8 +457,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               __syncwarp();
               const int n = n_base + c + hh * 16 + t_piece * 4;
               const bool col_ok = n < p.N;
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (bias_g && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(bias_g + n));
+              const float4 b4 = reinterpret_cast<const float4*>(wbias)[(c + hh * 16 + t_piece * 4) >> 2];
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int row = it * 8 + t_r8;
@@ -412,7 +466,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   const long long grow = out_row0 + row;
                   a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
                   if constexpr (EPI == EPI_F32_GELU_RESID) {
-                    a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+                    gelu_erf_x2(f2_pack(a.x, a.y), a.x, a.y);
+                    gelu_erf_x2(f2_pack(a.z, a.w), a.z, a.w);
                   }
                   if constexpr (HAS_RESID) {
                     a.x += rr[hh][it].x; a.y += rr[hh][it].y; a.z += rr[hh][it].z; a.w += rr[hh][it].w;
@@ -433,13 +488,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
 
-      // release the accumulator stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG == 2) mbar_arrive_cluster(tempty_leader0 + as * 8);
-        else mbar_arrive(&tempty[as]);
-      }
+      __syncwarp();   // every lane is done with this tile's bias slice
       if (C::ACC_STAGES == 2) {
         as ^= 1;
         if (as == 0) aph ^= 1;
@@ -608,7 +657,8 @@ int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
                "gemm: A strides must be multiples of 8 elements");
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
                "gemm: operands must be 16-byte aligned");
-  OASR_REQUIRE(a.N % 8 == 0 || a.epilogue == EPI_ARGMAX, "gemm: N must be a multiple of 8");
+  OASR_REQUIRE(a.N % 8 == 0 || (a.epilogue == EPI_ARGMAX && a.N % 4 == 0), "gemm: N must be a multiple of 8 (4 for arg-max)");
+  OASR_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
   if (a.epilogue != EPI_ARGMAX) {
     OASR_REQUIRE(a.out != nullptr && a.ldo >= a.N * a.groups, "gemm: output missing");
     OASR_REQUIRE(a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,

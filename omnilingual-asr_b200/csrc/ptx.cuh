@@ -270,6 +270,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// Same arrive without release semantics: no MEMBAR, so the thread does not wait for its outstanding global stores.
+// Only for hand-offs whose payload is ordered by other means (TMEM reads: tcgen05.wait::ld + fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 // TMA loads whose completion bytes are credited to a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* m, uint32_t cluster_bar_addr, int c0,
                                                 int c1, int c2) {
@@ -366,6 +371,64 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// The same packed operations on a 64-bit carrier (an aligned register pair), for code that keeps whole chains packed.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_pack_u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 f2_splat(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf on a packed pair (GEMM epilogues).  Same erfc(t) = 2^(-q(t)) form as gelu_erf, with the 1/sqrt 2 of
+// t = |x|/sqrt 2, the minus sign and the factor 1/2 folded into the polynomial: with u = min(|x|, 5.5 sqrt 2),
+//   erfc(u/sqrt 2)/2 = 2^(P(u) u - 1),   gelu(x) = max(x, 0) - |x| 2^(P(u) u - 1).
+// 10 FFMA2 + 2 MUFU + 6 scalar ops per PAIR; accuracy as gelu_erf (max abs error 2.9e-7).
+__device__ __forceinline__ void gelu_erf_x2(f32x2 x, float& y0, float& y1) {
+  float x0, x1;
+  f2_unpack(x, x0, x1);
+  const f32x2 u = f2_pack(fminf(fabsf(x0), 7.7781744f), fminf(fabsf(x1), 7.7781744f));
+  f32x2 q = f2_splat(-3.261924163e-09f);
+  q = f2_fma(q, u, f2_splat(1.316892713e-07f));
+  q = f2_fma(q, u, f2_splat(-2.183751327e-06f));
+  q = f2_fma(q, u, f2_splat(1.775559166e-05f));
+  q = f2_fma(q, u, f2_splat(-4.289695840e-05f));
+  q = f2_fma(q, u, f2_splat(-5.894688416e-04f));
+  q = f2_fma(q, u, f2_splat(7.835271108e-03f));
+  q = f2_fma(q, u, f2_splat(-5.320052363e-02f));
+  q = f2_fma(q, u, f2_splat(-4.589020233e-01f));
+  q = f2_fma(q, u, f2_splat(-1.151150320e+00f));
+  float a0, a1, e0, e1;
+  f2_unpack(f2_fma(q, u, f2_splat(-1.0f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  y0 = fmaf(-fabsf(x0), e0, fmaxf(x0, 0.f));
+  y1 = fmaf(-fabsf(x1), e1, fmaxf(x1, 0.f));
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
