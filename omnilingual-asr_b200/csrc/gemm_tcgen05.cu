@@ -139,27 +139,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
+      // This single thread must issue one stage per ~512 MMA cycles: the loop carries its coordinates incrementally
+      // (no division, nothing recomputed per k-block) - a 113-instruction body with two integer divisions measured
+      // ~675 cycles per iteration and starved the tensor pipe (profiles/r1_notes.md).
+      const int n_boxes = (BN > 256 && p.N > 256) ? 2 : 1;   // W boxes per stage
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
+        const int w_row = t.n_tile * BN + (CG == 2 ? cta_rank * p.b_box_rows : 0);
+        int par = 0, pos = t.m0, c0 = 0, wk = 0;   // parity / position / column of the current tap, K offset in W
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sA = smem + s * C::STAGE_BYTES;
           uint8_t* sB = sA + C::A_BYTES;
-          const int tap = kb / p.kb_per_tap;
-          const int c0 = (kb - tap * p.kb_per_tap) * BK;
           if constexpr (CG == 2) {
             // both CTAs' bytes are credited to the leader's barrier, which the leader arms for the pair
             const uint32_t bar = mapa_u32(smem_u32(&full[s]), 0);
             if (leader) mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
-            tma_load_5d_cg2(sA, &tmA, bar, c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
-            for (int j = 0; j < BN && j < p.N; j += 256)
-              tma_load_3d_cg2(sB + (j / 2) * (BK * 2), &tmB, bar, kb * BK,
-                              t.n_tile * BN + j + cta_rank * p.b_box_rows, t.g);
+            tma_load_5d_cg2(sA, &tmA, bar, c0, par, pos, t.b, t.g);
+            tma_load_3d_cg2(sB, &tmB, bar, wk, w_row, t.g);
+            if (n_boxes == 2) tma_load_3d_cg2(sB + 128 * (BK * 2), &tmB, bar, wk, w_row + 256, t.g);
           } else {
             mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
-            tma_load_5d(sA, &tmA, &full[s], c0, tap % p.P, t.m0 + tap / p.P, t.b, t.g);
-            for (int j = 0; j < BN && j < p.N; j += p.b_box_rows)
-              tma_load_3d(sB + j * (BK * 2), &tmB, &full[s], kb * BK, t.n_tile * BN + j, t.g);
+            tma_load_5d(sA, &tmA, &full[s], c0, par, pos, t.b, t.g);
+            tma_load_3d(sB, &tmB, &full[s], wk, w_row, t.g);
+            if (n_boxes == 2) tma_load_3d(sB + 256 * (BK * 2), &tmB, &full[s], wk, w_row + 256, t.g);
+          }
+          wk += BK;
+          c0 += BK;
+          if (c0 == p.kb_per_tap * BK) {   // next tap
+            c0 = 0;
+            if (++par == p.P) {
+              par = 0;
+              ++pos;
+            }
           }
           if (++s == C::STAGES) {
             s = 0;
