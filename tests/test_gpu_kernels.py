@@ -206,7 +206,9 @@ def test_posconv(device, gen, d, groups, k, T, B):
 
 # ------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("H,hd,T,B,ragged", [(4, 64, 300, 2, False), (4, 80, 300, 2, True), (2, 128, 257, 2, True),
-                                             (16, 80, 1499, 1, False), (3, 16, 100, 1, False)])
+                                             (16, 80, 1499, 1, False), (3, 16, 100, 1, False),
+                                             (2, 96, 400, 2, True), (2, 112, 333, 2, True), (2, 128, 1499, 1, False),
+                                             (2, 32, 129, 1, False), (2, 48, 515, 2, True)])
 def test_attention(device, gen, H, hd, T, B, ragged):
     d = H * hd
     qkv = _rand((B * T, 3 * d), gen).bfloat16()
@@ -237,12 +239,14 @@ def test_attention(device, gen, H, hd, T, B, ragged):
     assert rel_err(o[0], ref2[0]) < 1e-2
 
 
-def test_attention_growing_scores_take_the_rescale_path(device, gen):
-    """Keys whose scores grow along the sequence push the running reference up by > 2^8 several times."""
-    H, hd, T, B = 2, 64, 700, 1
+@pytest.mark.parametrize("hd,top", [(64, 6.0), (64, 30.0), (80, 30.0), (128, 24.0)])
+def test_attention_growing_scores_take_the_rescale_path(device, gen, hd, top):
+    """Keys whose scores grow along the sequence push the running reference up several times (top = 30: by far more
+    than the 2^80 margin, within a block and across blocks)."""
+    H, T, B = 2, 700, 1
     d = H * hd
     qkv = _rand((B * T, 3 * d), gen, 0.5)
-    ramp = torch.linspace(0.0, 6.0, T, device=device)
+    ramp = torch.linspace(0.0, top, T, device=device)
     qkv[:, :d] = 1.0 + 0.1 * qkv[:, :d]                       # q ~ all ones
     qkv[:, d:2 * d] = ramp[:, None] + 0.1 * qkv[:, d:2 * d]   # k grows with the position
     qkv = qkv.bfloat16()
