@@ -48,20 +48,29 @@ struct GemmKernelParams {
 
 // CG = CTAs cooperating on one tile (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile with each
 // CTA holding 128 rows of A, half of the B rows and 128 rows of the accumulator.
-template <int BN, int CG = 1>
+constexpr bool epi_has_resid(int epi) { return epi == EPI_F32_RESID || epi == EPI_F32_GELU_RESID; }
+
+template <int BN, int CG, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
   static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
   static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int UMMA_N = BN > 256 ? 256 : BN;
-  static constexpr int BAR_BYTES = 4096;  // barriers (<256 B) + LN reduction scratch (2 KB at +256)
-  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * 20 * 4;  // per-warp [32][20] word transpose buffers
+  static constexpr int BAR_BYTES = 4096;  // barriers (<256 B), LN reduction scratch (2 KB at +256), epilogue barriers (+2304)
+  // epilogue staging: per-warp [32][20] word transpose buffers, or (residual epilogues) per warp two 64B-swizzled
+  // [32 rows][RES_CW fp32] tiles that TMA fills with the residual and stores back as the output (16 columns: 32 KB
+  // in all, which leaves five ring stages; 32-column tiles left four and cost FFN2, K = 5120, 3 %)
+  static constexpr int RES_CW = 16;
+  static constexpr int RES_TILE_BYTES = 32 * RES_CW * 4;
+  static constexpr int EPI_STAGE_BYTES = epi_has_resid(EPI) ? EPI_WARPS * 2 * RES_TILE_BYTES : EPI_WARPS * 32 * 20 * 4;
   static constexpr int EPI_PARAM_BYTES = 8192;  // per-warp bias slices [8][128] f32, or bias|gamma|beta [3][512] (LN)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + EPI_STAGE_BYTES + EPI_PARAM_BYTES + 1024 /*align slack*/;
+  static constexpr int FIXED_BYTES = BAR_BYTES + EPI_STAGE_BYTES + EPI_PARAM_BYTES + 1024 /*align slack*/;
+  static constexpr int STAGES_RAW = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 struct TileCoord {
@@ -82,8 +91,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKernelParams& p, int 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const GemmKernelParams p) {
-  using C = GemmCfg<BN, CG>;
+            const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const GemmKernelParams p) {
+  using C = GemmCfg<BN, CG, EPI>;
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
   const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -101,6 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int STAGE_LD = 20;                             // words per staged row: 16 payload + 4 pad (80 B)
   uint32_t* stage = reinterpret_cast<uint32_t*>(bar_base + C::BAR_BYTES) + ((threadIdx.x >> 5) & 7) * (32 * STAGE_LD);
   float* epi_params = reinterpret_cast<float*>(bar_base + C::BAR_BYTES + C::EPI_STAGE_BYTES);
+  uint64_t* res_full = reinterpret_cast<uint64_t*>(bar_base + 2304);   // [EPI_WARPS][2], residual epilogues only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +128,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
+    if constexpr (epi_has_resid(EPI))
+      for (int a = 0; a < EPI_WARPS * 2; ++a) mbar_init(&res_full[a], 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -269,6 +281,44 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    // Residual epilogues (out-proj, FFN2, pos-conv) never touch global memory from the epilogue threads: per warp,
+    // TMA brings the residual of a [32 rows x 16 columns] chunk into a 64B-swizzled shared tile one chunk ahead
+    // (across tile boundaries too), the threads add accumulator + bias (+GELU) in place - row per thread, the TMEM
+    // layout - and TMA stores the tile as the output.  Completion is tracked by mbarriers / bulk groups, not by the
+    // warp's load scoreboards (a register prefetch of the next chunk was serialised by them: profiles/r1_notes.md).
+    // out may alias resid: a chunk is loaded, then stored, by the same warp, and no other tile touches it.
+    constexpr bool HAS_RESID = epi_has_resid(EPI);
+    uint8_t* res_buf = reinterpret_cast<uint8_t*>(bar_base + C::BAR_BYTES) + (warp - 4) * (2 * C::RES_TILE_BYTES);
+    uint64_t* my_res_full = res_full + (warp - 4) * 2;
+    int res_g = 0;                 // chunks consumed so far: buffer res_g & 1, barrier parity (res_g >> 1) & 1
+    int pf_tile = first_tile, pf_ci = 0;   // next chunk to request
+    auto chunk_valid = [&](int tile_i, int ci) {
+      return (tile_i % p.n_tiles) * BN + half * (BN / 2) + ci * C::RES_CW < p.N;
+    };
+    auto pf_skip_invalid = [&]() {
+      while (pf_tile < p.total_tiles && !chunk_valid(pf_tile, pf_ci)) {
+        if (++pf_ci == (BN / 2) / C::RES_CW) {
+          pf_ci = 0;
+          pf_tile += tile_step;
+        }
+      }
+    };
+    auto pf_issue = [&](int buf) {   // lane 0: request the next valid chunk into buffer `buf`
+      pf_skip_invalid();
+      if (pf_tile < p.total_tiles) {
+        const TileCoord t = decode_tile<CG>(p, pf_tile, cta_rank);
+        mbar_arrive_expect_tx(&my_res_full[buf], C::RES_TILE_BYTES);
+        tma_load_4d(res_buf + buf * C::RES_TILE_BYTES, &tmR, &my_res_full[buf], t.n_tile * BN + half * (BN / 2) + pf_ci * C::RES_CW,
+                    t.g, t.m0 + q * 32, t.b);
+        if (++pf_ci == (BN / 2) / C::RES_CW) {
+          pf_ci = 0;
+          pf_tile += tile_step;
+        }
+      }
+    };
+    if constexpr (HAS_RESID) {
+      if (lane == 0) pf_issue(0);
+    }
     for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile<CG>(p, tile, cta_rank);
       const int row_in_tile = q * 32 + lane;
@@ -433,27 +483,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }, true);
       } else {
-        // fp32 outputs: EPI_F32 / EPI_F32_RESID / EPI_F32_GELU_RESID, 16 columns per transpose round
-        constexpr bool HAS_RESID = (EPI == EPI_F32_RESID || EPI == EPI_F32_GELU_RESID);
+        if constexpr (HAS_RESID) {
+          constexpr int CW = C::RES_CW;
+          constexpr int NCH = HALF_N / CW;
 #pragma unroll 1
-        for (int c = 0; c < HALF_N; c += 32) {
-          // The residual of the whole 32-column chunk is requested first (8 independent 16-byte loads per lane),
-          // so that its HBM latency overlaps the TMEM read and the transpose.  out may alias resid: every element
-          // is read and written by the same lane, reads of a chunk are issued before any of its writes.
-          float4 rr[2][4];
-          if constexpr (HAS_RESID) {
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int n = n_base + c + hh * 16 + t_piece * 4;
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int row = it * 8 + t_r8;
-                rr[hh][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row < rows_valid && n < p.N)
-                  rr[hh][it] = *reinterpret_cast<const float4*>(p.resid + (out_row0 + row) * p.ldo + gcol + n);
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int c = ci * CW;
+            uint32_t v[CW];
+            tmem_ld16(t_base + c, v);
+            if (n_base + c < p.N) {   // warp-uniform
+              const int buf = res_g & 1;
+              if (lane == 0) {
+                // the other buffer was handed to a TMA store one chunk ago: wait until that store has read it, then
+                // request the next chunk into it
+                bulk_wait_group_read<0>();
+                pf_issue(buf ^ 1);
               }
+              tmem_ld_wait();
+              if (ci + 1 == NCH) release_acc();
+              mbar_wait(&my_res_full[buf], (res_g >> 1) & 1);
+              uint8_t* row = res_buf + buf * C::RES_TILE_BYTES + lane * (CW * 4);
+#pragma unroll
+              for (int k = 0; k < CW / 4; ++k) {
+                float4* cell = reinterpret_cast<float4*>(row + ((k ^ ((lane >> 1) & 3)) << 4));   // 64B swizzle
+                const float4 r4 = *cell;
+                const float4 b4 = reinterpret_cast<const float4*>(wbias)[(c >> 2) + k];
+                float4 a;
+                a.x = __uint_as_float(v[4 * k]) + b4.x;
+                a.y = __uint_as_float(v[4 * k + 1]) + b4.y;
+                a.z = __uint_as_float(v[4 * k + 2]) + b4.z;
+                a.w = __uint_as_float(v[4 * k + 3]) + b4.w;
+                if constexpr (EPI == EPI_F32_GELU_RESID) {
+                  gelu_erf_x2(f2_pack(a.x, a.y), a.x, a.y);
+                  gelu_erf_x2(f2_pack(a.z, a.w), a.z, a.w);
+                }
+                a.x += r4.x; a.y += r4.y; a.z += r4.z; a.w += r4.w;
+                *cell = a;
+              }
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmO, res_buf + buf * C::RES_TILE_BYTES, n_base + c, tc.g, tc.m0 + q * 32, tc.b);
+                bulk_commit_group();
+              }
+              ++res_g;
+            } else {
+              tmem_ld_wait();
+              if (ci + 1 == NCH) release_acc();
             }
           }
+        } else {
+        // fp32 output without residual (EPI_F32), 16 columns per transpose round
+#pragma unroll 1
+        for (int c = 0; c < HALF_N; c += 32) {
           uint32_t v[32];
           tmem_ld32(t_base + c, v);
           tmem_ld_wait();
@@ -477,19 +559,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (row < rows_valid && col_ok) {
                   const long long grow = out_row0 + row;
                   a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-                  if constexpr (EPI == EPI_F32_GELU_RESID) {
-                    gelu_erf_x2(f2_pack(a.x, a.y), a.x, a.y);
-                    gelu_erf_x2(f2_pack(a.z, a.w), a.z, a.w);
-                  }
-                  if constexpr (HAS_RESID) {
-                    a.x += rr[hh][it].x; a.y += rr[hh][it].y; a.z += rr[hh][it].z; a.w += rr[hh][it].w;
-                  }
-                  if constexpr (EPI == EPI_F32) {
-                    if (p.n_valid != nullptr) {
-                      const int seq = int(grow / p.frames_per_seq);
-                      const int t = int(grow - (long long)seq * p.frames_per_seq);
-                      if (t >= __ldg(p.n_valid + seq)) a = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                  if (p.n_valid != nullptr) {
+                    const int seq = int(grow / p.frames_per_seq);
+                    const int t = int(grow - (long long)seq * p.frames_per_seq);
+                    if (t >= __ldg(p.n_valid + seq)) a = make_float4(0.f, 0.f, 0.f, 0.f);
                   }
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + grow * p.ldo + gcol + n) = a;
                 }
@@ -497,6 +570,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               __syncwarp();
             }
           }
+        }
         }
       }
 
@@ -507,6 +581,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else {
         aph ^= 1;
       }
+    }
+    if constexpr (HAS_RESID) {
+      if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last TMA store's read
     }
   }
 
@@ -525,12 +602,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 struct TmapKey {
   const void* base;
   int rank;
+  bool f32;
+  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B;
   uint64_t dims[5];
   uint64_t strides[4];
   uint32_t box[5];
   bool operator<(const TmapKey& o) const {
     if (base != o.base) return base < o.base;
     if (rank != o.rank) return rank < o.rank;
+    if (f32 != o.f32) return f32 < o.f32;
+    if (swizzle != o.swizzle) return swizzle < o.swizzle;
     for (int i = 0; i < 5; ++i) if (dims[i] != o.dims[i]) return dims[i] < o.dims[i];
     for (int i = 0; i < 4; ++i) if (strides[i] != o.strides[i]) return strides[i] < o.strides[i];
     for (int i = 0; i < 5; ++i) if (box[i] != o.box[i]) return box[i] < o.box[i];
@@ -547,7 +628,7 @@ int cached_tmap(CUtensorMap* out, const TmapKey& key) {
     *out = it->second;
     return OASR_OK;
   }
-  OASR_TRY(make_tmap_bf16(out, key.base, key.rank, key.dims, key.strides, key.box, CU_TENSOR_MAP_SWIZZLE_128B));
+  OASR_TRY(make_tmap(out, key.base, key.f32, key.rank, key.dims, key.strides, key.box, key.swizzle));
   if (g_tmap_cache.size() > 8192) g_tmap_cache.clear();
   g_tmap_cache[key] = *out;
   return OASR_OK;
@@ -557,7 +638,7 @@ inline uint64_t nz(long long v, uint64_t fallback) { return v > 0 ? (uint64_t)v 
 
 template <int BN, int EPI, int CG>
 int launch_cg(const GemmArgs& a, cudaStream_t stream) {
-  using C = GemmCfg<BN, CG>;
+  using C = GemmCfg<BN, CG, EPI>;
   const int k_pad = a.k_pad > 0 ? a.k_pad : ((a.a_inner + BK - 1) / BK) * BK;
   GemmKernelParams p;
   p.rows_per_batch = a.rows_per_batch;
@@ -610,6 +691,27 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   OASR_TRY(cached_tmap(&tmA, ka));
   OASR_TRY(cached_tmap(&tmB, kw));
+  CUtensorMap tmR = tmA, tmO = tmA;   // placeholders unless the epilogue moves fp32 tiles through TMA
+  if constexpr (epi_has_resid(EPI)) {
+    // fp32 {N, groups, rows_per_batch, batches}: a [32 rows x 16 columns] box is clipped at the group's last column
+    // and at the batch's last row (no write beyond either), 64B swizzle
+    const void* bases[2] = {a.resid, a.out};
+    CUtensorMap* maps[2] = {&tmR, &tmO};
+    for (int i = 0; i < 2; ++i) {
+      TmapKey kr{};
+      kr.base = bases[i];
+      kr.rank = 4;
+      kr.f32 = true;
+      kr.dims[0] = (uint64_t)a.N; kr.dims[1] = (uint64_t)a.groups; kr.dims[2] = (uint64_t)a.rows_per_batch;
+      kr.dims[3] = (uint64_t)a.batches;
+      kr.strides[0] = (uint64_t)a.N * 4;
+      kr.strides[1] = (uint64_t)a.ldo * 4;
+      kr.strides[2] = (uint64_t)p.out_batch_rows * a.ldo * 4;
+      kr.box[0] = C::RES_CW; kr.box[1] = 1; kr.box[2] = 32; kr.box[3] = 1;
+      kr.swizzle = CU_TENSOR_MAP_SWIZZLE_64B;
+      OASR_TRY(cached_tmap(maps[i], kr));
+    }
+  }
 
   static bool attr_done = false;
   if (!attr_done) {
@@ -632,9 +734,9 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG>, tmA, tmB, p));
+    OASR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EPI, CG>, tmA, tmB, tmR, tmO, p));
   } else {
-    gemm_kernel<BN, EPI, CG><<<grid_units, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_kernel<BN, EPI, CG><<<grid_units, GEMM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, tmR, tmO, p);
   }
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;

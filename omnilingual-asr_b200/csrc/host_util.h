@@ -40,4 +40,8 @@ int device_sm_count();
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// same for bf16 (f32 = false) or fp32 elements
+int make_tmap(CUtensorMap* out, const void* base, bool f32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
 }  // namespace oasr

@@ -175,8 +175,10 @@ fe_layer0_kernel(const float* __restrict__ wave, long long in_stride, int T0, co
 // Row LayerNorm: one warp per row, the row lives in registers as float4 groups (lane owns groups
 // lane + 32 j).  D % 4 == 0, D <= 2048.  16-byte loads, 8/16-byte stores, two-pass fp32 statistics.
 // ---------------------------------------------------------------------------------------------
-template <bool IN_BF16>
-__global__ void __launch_bounds__(256)
+// MAXJ = float4 groups per lane (D <= 128 * MAXJ): sized to the row so that the register count allows three or
+// four 256-thread blocks per SM; the kernel is HBM-bound and needs the loads of many rows in flight.
+template <bool IN_BF16, int MAXJ>
+__global__ void __launch_bounds__(256, MAXJ <= 10 ? 3 : 2)
 layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int batches, int rows_per_batch, int D,
                  const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
                  float* __restrict__ out_f32) {
@@ -187,7 +189,6 @@ layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int bat
   const int b = int(row / rows_per_batch);
   const int t = int(row - (long long)b * rows_per_batch);
   const int ngroups = D >> 2;  // float4 groups in the row
-  constexpr int MAXJ = 16;
   float4 v[MAXJ];
   float s = 0.f;
   if (IN_BF16) {
@@ -306,12 +307,19 @@ int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, in
   if (total == 0) return OASR_OK;
   const int rows_per_block = 8;
   const unsigned grid = (unsigned)((total + rows_per_block - 1) / rows_per_block);
-  if (in_is_bf16)
-    layernorm_kernel<true><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,
-                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
-  else
-    layernorm_kernel<false><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,
-                                                      reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
+#define OASR_LN_LAUNCH(BF, MJ)                                                                                  \
+  layernorm_kernel<BF, MJ><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,   \
+                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32)
+  if (in_is_bf16) {
+    if (D <= 512) OASR_LN_LAUNCH(true, 4);
+    else if (D <= 1280) OASR_LN_LAUNCH(true, 10);
+    else OASR_LN_LAUNCH(true, 16);
+  } else {
+    if (D <= 512) OASR_LN_LAUNCH(false, 4);
+    else if (D <= 1280) OASR_LN_LAUNCH(false, 10);
+    else OASR_LN_LAUNCH(false, 16);
+  }
+#undef OASR_LN_LAUNCH
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }
