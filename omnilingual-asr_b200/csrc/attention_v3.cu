@@ -545,6 +545,7 @@ int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T
   if (version == 1) return attention_bf16_v1(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version == 2) return attention_bf16_v2(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version == 3) return attention_bf16_v3(qkv, out, n_frames, B, T, H, hd, scale, stream);
+  if (version == 5) return attention_bf16_v5(qkv, out, n_frames, B, T, H, hd, scale, stream);   // experiment, see v5
   return attention_bf16_v4(qkv, out, n_frames, B, T, H, hd, scale, stream);
 }
 

@@ -1,22 +1,23 @@
-// Bidirectional self-attention on tcgen05, fourth version (a14).  Same numerics contract and tile scheme as v3
-// (one (sequence, head, PAIR of 128-query tiles) per CTA, one pass over the keys, integer log2-domain softmax
-// reference so that a reference move rescales by an exact power of two), but the two MMAs of a key block are
-// decoupled so that the softmax warps - the MUFU.EX2 pipe is the floor of this kernel - never wait for the tensor
-// pipe (v3 timeline, profiles/r1_notes.md: softmax 1700 cycles, then 440 hand-off + 975 for P.V(j) and S(j+1) with
-// the softmax warps idle, because P was aliased onto S and S(j+1) could not start before P.V(j) had consumed P(j)):
+// Bidirectional self-attention on tcgen05, fifth version (a14): v4's pipeline (P in its own TMEM columns, S(j+1)
+// issued as soon as S(j) has been read, one pass over the keys, integer log2-domain softmax reference) with SIXTEEN
+// softmax warps instead of eight: four per SM sub-partition.  Measured on B200 (scripts/ubench/softmax_pattern.cu) the
+// softmax instruction pattern sustains one MUFU.EX2 per 10.6 / 9.2 / 8.3 cycles with 1 / 2 / 4 warps per sub-partition
+// (pipe limit 8.0), and with two warps the fixed per-block work of a warp (TMEM loads and stores, fences, barrier
+// round trips: ~450 cycles) leaves the MUFU pipe idle a third of the time (v4 timeline, profiles/r1_notes.md).
 //
-//   * P has its own TMEM columns.  The key block is shortened so that 2 S + 2 P + 2 O fit the 512 columns:
-//     BKV = 128 (head_dim <= 64), 96 (<= 96), 80 (<= 128).
-//   * The softmax warps signal `s_free` as soon as the LAST chunk of S(j) is in registers (after 1/3 - 1/2 of the
-//     block's exponentials); the MMA thread then issues S(j+1) = Q K_{j+1}^T, which is ready long before softmax(j)
-//     ends.  P.V(j) is issued when P(j) has been written and runs under softmax(j+1).
-//   * The softmax reference is checked per 32-column chunk on the raw scores (one FMNMX per score; the block can no
-//     longer be redone from S): a chunk whose maximum exceeds the reference by more than 2^80 moves it; the rare
-//     path rescales the running sum, the P values of the block computed so far (bf16 x 2^-k is exact) and O in TMEM.
+// Every query row is therefore shared by TWO warps: warp "lo" takes the first half of the key block's columns, warp
+// "hi" the second half (both address the same TMEM lanes: warp id % 4 is the row group).  Per block the pair
+//   1. loads its half of S(j) into registers and hands S back (s_free),
+//   2. exchanges the per-row maximum of its half through shared memory (named barrier of the 64 threads) and so
+//      derives the SAME reference decision: the reference moves when the block maximum exceeds it by more than 2^80
+//      (both scale their partial row sums, the lo warp rescales O in TMEM),
+//   3. computes P = 2^(s c - m_ref) for its columns, writes it to its half of the P columns and arrives on p_full.
+// The row sum is the sum of the two partial sums (exchanged once, at the end); the epilogue splits the head
+// dimension between the two warps.
 //
-// TMEM columns: S_A [0,BKV) S_B [BKV,2BKV) P_A, P_B (BKV/2 rounded up to 16 each) O_A, O_B (head_dim each).
-// Warps: 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w owns TMEM lanes [32(w%4), +32)), 8 TMA producer,
-// 9 MMA issuer / TMEM allocator.
+// Key block: BKV = 96 (head_dim <= 96) or 80, so that 2 S + 2 P + 2 O fit 512 TMEM columns and a warp's half block
+// (48 / 40 scores + 24 / 20 packed P words) fits the 112 registers a 576-thread CTA leaves per thread.
+// Warps: 0-3 tile A lo, 4-7 tile A hi, 8-11 tile B lo, 12-15 tile B hi, 16 TMA producer, 17 MMA issuer / TMEM allocator.
 #include "host_util.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -28,13 +29,14 @@
 namespace oasr {
 namespace {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 576;
+constexpr int SOFTMAX_WARPS = 16;
 constexpr int BQ = 128;
 constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
-constexpr float REF_MARGIN = 80.f;   // a chunk maximum more than 2^80 above the reference moves the reference
+constexpr float REF_MARGIN = 80.f;   // a block maximum more than 2^80 above the reference moves the reference
 
-__host__ __device__ constexpr int att_bkv(int hd) { return hd <= 64 ? 128 : (hd <= 96 ? 96 : 80); }
+__host__ __device__ constexpr int att_bkv(int hd) { return hd <= 96 ? 96 : 80; }
 __host__ __device__ constexpr int round16(int v) { return (v + 15) & ~15; }
 
 // Column chunks of a [rows][HD] bf16 K-major tile: greedy 64 / 32 / 16 (128B / 64B / 32B swizzle); see v3.
@@ -69,7 +71,7 @@ __host__ __device__ constexpr uint32_t desc_hi(int sbo_bytes, uint32_t layout) {
 }
 __device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
 
-struct Attn4Params {
+struct Attn5Params {
   int kv_stages;
   int T, H, d;
   float scale_log2e;
@@ -77,7 +79,7 @@ struct Attn4Params {
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
 };
-constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (tile A), 2 softmax warp 4 (tile B)
+constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (tile A lo), 2 softmax warp 8 (tile B lo)
 #define ATT_TRACE(role, ev)                                                                                 \
   do {                                                                                                      \
     if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (ev) < TRACE_EVENTS) \
@@ -89,116 +91,46 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t bf16x2_scale(uint32_t v, uint32_t f2) {
-  uint32_t r;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(f2));
-  return r;
-}
 
-// 2^x for a packed pair on the FMA pipe (no MUFU): Cody-Waite split with the round-to-nearest magic constant,
-// degree-4 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.7e-6, a 1/1400 of a bf16 ulp), exponent inserted
-// with one integer multiply-add per element.  x must be in [-126, 127].
-__device__ __forceinline__ float2 exp2_fma2(float2 x) {
-  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));          // low mantissa bits = round(x)
-  const float2 xi = fadd2(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = ffma2(xi, make_float2(-1.f, -1.f), x);
-  float2 q = ffma2(make_float2(9.570069611e-03f, 9.570069611e-03f), f, make_float2(5.591785908e-02f, 5.591785908e-02f));
-  q = ffma2(q, f, make_float2(2.402474582e-01f, 2.402474582e-01f));
-  q = ffma2(q, f, make_float2(6.931217909e-01f, 6.931217909e-01f));
-  q = ffma2(q, f, make_float2(9.999992847e-01f, 9.999992847e-01f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
-// Everything a reference move has to touch.
-template <int HD>
-struct RowState {
-  float m_ref;       // integer-valued reference in the log2 domain
-  float sum;         // running sum of the unrounded P of finished blocks
-  float2 sm[2];      // pair-accumulators of the block in flight
-  uint32_t t_o;      // TMEM address of this row's O
-  uint64_t* o_done;  // P.V_X(j) has retired
-  int j;             // key block in flight
-};
-
-// Moves the reference of the rows whose `need` = chunk maximum (log2 domain) - m_ref exceeds REF_MARGIN.  NPK =
-// packed P words of the block computed so far.  Warp-collective (TMEM accesses): called under a warp-uniform branch.
-template <int HD, int NPK, int PKN>
-__device__ __forceinline__ void move_reference(float need, RowState<HD>& rs, uint32_t (&pk)[PKN]) {
-  const float k = need > REF_MARGIN ? ceilf(need) : 0.f;
-  const float f = ex2(-k);   // exact (k is an integer); 0 when the old reference was hopelessly low
-  rs.m_ref += k;
-  rs.sum *= f;
-  rs.sm[0].x *= f; rs.sm[0].y *= f; rs.sm[1].x *= f; rs.sm[1].y *= f;
-  const uint32_t f2 = pack_bf16x2(f, f);
-#pragma unroll
-  for (int i = 0; i < NPK; ++i) pk[i] = bf16x2_scale(pk[i], f2);
-  if (rs.j > 0) {
-    mbar_wait(rs.o_done, (rs.j - 1) & 1);   // P.V(j-1) has finished updating O; P.V(j) cannot start before our p_full
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < HD; cc += 16) {
-      uint32_t v[16];
-      tmem_ld16(rs.t_o + cc, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-      tmem_st16(rs.t_o + cc, v);
-    }
-    tmem_st_wait();
-  }
-}
-
-// W scores of a row (columns [BASE, BASE+W) of the block): reference check, P = 2^(s c - m_ref) -> pk, sums.
-// POLY > 0: every POLY-th pair takes the FMA-pipe exponential instead of MUFU.EX2 (the MUFU pipe is the floor of the
-// kernel: two softmax warps per SM sub-partition cannot issue more than ~1 MUFU per 10 cycles between them).
-template <int HD, int BASE, int W, bool MASKED, int POLY, int PKN>
-__device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, float c, RowState<HD>& rs,
-                                              uint32_t (&pk)[PKN]) {
-  float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+// maximum of the first nv of W scores (four independent chains)
+template <int W, bool MASKED>
+__device__ __forceinline__ float chunk_max(const uint32_t* v, int nv) {
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int i = 0; i < W; ++i)
-    if (!MASKED || BASE + i < ncols) cm4[(i >> 1) & 3] = fmaxf(cm4[(i >> 1) & 3], __uint_as_float(v[i]));
-  const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
-  if (BASE == 0 && rs.j == 0) {
-    rs.m_ref = ceilf(cm * c);   // first chunk of the row (column 0 is always a valid key)
-  } else {
-    const float need = fmaf(cm, c, -rs.m_ref);
-    if (__any_sync(0xffffffffu, need > REF_MARGIN)) move_reference<HD, BASE / 2>(need, rs, pk);
-  }
-  const float2 c2 = make_float2(c, c), nm2 = make_float2(-rs.m_ref, -rs.m_ref);
+    if (!MASKED || i < nv) m4[(i >> 1) & 3] = fmaxf(m4[(i >> 1) & 3], __uint_as_float(v[i]));
+  return fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+}
+
+// W scores -> P = 2^(s c - m_ref), packed to bf16 into pk[PK0 ...], unrounded P accumulated in sm
+template <int W, int PK0, bool MASKED, int PKN>
+__device__ __forceinline__ void chunk_exp(const uint32_t* v, int nv, float2 c2, float2 nm2, float2 (&sm)[2],
+                                          uint32_t (&pk)[PKN]) {
 #pragma unroll
   for (int i = 0; i < W; i += 2) {
     const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
-    float p0, p1;
-    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-      const float2 e = exp2_fma2(make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f)));
-      p0 = e.x;
-      p1 = e.y;
-    } else {
-      p0 = ex2(x.x);
-      p1 = ex2(x.y);
-    }
+    float p0 = ex2(x.x), p1 = ex2(x.y);
     if (MASKED) {
-      if (BASE + i >= ncols) p0 = 0.f;
-      if (BASE + i + 1 >= ncols) p1 = 0.f;
+      if (i >= nv) p0 = 0.f;
+      if (i + 1 >= nv) p1 = 0.f;
     }
-    rs.sm[(i >> 1) & 1] = fadd2(rs.sm[(i >> 1) & 1], make_float2(p0, p1));
-    pk[(BASE + i) >> 1] = pack_bf16x2(p0, p1);
+    sm[(i >> 1) & 1] = fadd2(sm[(i >> 1) & 1], make_float2(p0, p1));
+    pk[PK0 + (i >> 1)] = pack_bf16x2(p0, p1);
   }
 }
 
-template <int HD, int POLY>
+template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
+attention_v5_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
                     const __grid_constant__ CUtensorMap tmk32, const __grid_constant__ CUtensorMap tmk16,
-                    const Attn4Params p) {
+                    const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BKV = att_bkv(HD);
+  constexpr int HW = BKV / 2;          // score columns per softmax warp: 48 or 40
+  constexpr int PW = HW / 2;           // packed P words per softmax warp: 24 or 20
+  constexpr int TAILW = HW - 32;       // 16 or 8
   constexpr int PSLOT = round16(BKV / 2);
   constexpr int TM_S = 0, TM_P = 2 * BKV, TM_O = 2 * BKV + 2 * PSLOT;
   static_assert(TM_O + 2 * HD <= TMEM_COLS, "TMEM budget");
@@ -215,10 +147,12 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   uint64_t* kv_full = bars + 1;                  // MAX_KV_STAGES
   uint64_t* kv_empty = kv_full + MAX_KV_STAGES;  // MAX_KV_STAGES
   uint64_t* s_full = kv_empty + MAX_KV_STAGES;   // 2 (per query tile): S_X(j) is in TMEM
-  uint64_t* s_free = s_full + 2;                 // 2: S_X(j) has been read into registers
-  uint64_t* p_full = s_free + 2;                 // 2: P_X(j) is in TMEM
+  uint64_t* s_free = s_full + 2;                 // 2: S_X(j) has been read into registers (8 warps)
+  uint64_t* p_full = s_free + 2;                 // 2: P_X(j) is in TMEM (8 warps)
   uint64_t* o_done = p_full + 2;                 // 2: P.V_X(j) has retired (O updated, P buffer free)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* xch_max = reinterpret_cast<float*>(bars + 32);   // [2 parities][2 tiles][2 halves][128 rows]
+  float* xch_sum = xch_max + 2 * 2 * 2 * BQ;              // [2 tiles][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * BQ);
@@ -236,7 +170,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     return;
   }
 
-  if (warp == 8 && lane == 0) {
+  if (warp == SOFTMAX_WARPS && lane == 0) {
     tma_prefetch_desc(&tmq64);
     tma_prefetch_desc(&tmk64);
     tma_prefetch_desc(&tmq16);
@@ -248,13 +182,13 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&s_free[i], 8);
+      mbar_init(&p_full[i], 8);
       mbar_init(&o_done[i], 1);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == SOFTMAX_WARPS + 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
@@ -263,7 +197,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == SOFTMAX_WARPS) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       const int qcol = h * HD, kcol = p.d + h * HD, vcol = 2 * p.d + h * HD;
@@ -294,12 +228,11 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == SOFTMAX_WARPS + 1) {
+    // ---------------------------------------------------------------- MMA issuer (as v4)
     // Warp-uniform control flow; one elected lane issues.  Static order per key block j:
     //   p_full_B(j-1) -> P.V_B(j-1), release K/V(j-1);  s_free_A(j) -> S_A(j+1);  s_free_B(j) -> S_B(j+1);
     //   p_full_A(j) -> P.V_A(j)
-    // (the K/V release precedes the wait for block j+1 so that two stages are enough).
     const bool issuer = elect_one();
     constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
@@ -343,6 +276,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     mbar_wait(&kv_full[0], 0);
     tc_fence_after();
     issue_s(0, 0);
+    issue_s(1, 0);
     int st_prev = 0, st = 0, st_next = KS > 1 ? 1 : 0;
     uint32_t ph_next = KS > 1 ? 0u : 1u;   // kv_full parity of block j+1
     for (int j = 0; j < nblk; ++j) {
@@ -354,13 +288,10 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         if (issuer) umma_commit(&kv_empty[st_prev]);   // K/V of block j-1: every MMA reading them has been issued
         __syncwarp();
       }
-      if (more) mbar_wait(&kv_full[st_next], ph_next);
-      mbar_wait(&s_free[0], j & 1);
-      tc_fence_after();
-      // Tile B starts when tile A is through the TMEM reads of its first block, so that the exponential phases of
-      // the two softmax warps of an SM sub-partition alternate instead of colliding on the MUFU pipe.
-      if (j == 0) issue_s(1, 0);
       if (more) {
+        mbar_wait(&kv_full[st_next], ph_next);
+        mbar_wait(&s_free[0], j & 1);
+        tc_fence_after();
         issue_s(0, st_next);
         mbar_wait(&s_free[1], j & 1);
         tc_fence_after();
@@ -382,112 +313,120 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     tc_fence_after();
     issue_pv(1, st_prev, nblk - 1);
   } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 0-7)
-    const int X = warp >> 2;                     // query tile of this warpgroup
-    const int r = (warp & 3) * 32 + lane;        // row within the tile == TMEM lane
-    const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + TM_S + X * BKV;
-    const uint32_t t_p = t_lane + TM_P + X * PSLOT;
+    // ---------------------------------------------------------------- softmax + epilogue (warps 0-15)
+    const int X = warp >> 3;                     // query tile
+    const int half = (warp >> 2) & 1;            // column half of the key block
+    const int rg = warp & 3;                     // row group == TMEM lane quarter
+    const int r = rg * 32 + lane;                // row within the tile == TMEM lane
+    const int pair_bar = 1 + X * 4 + rg;         // named barrier of the two warps sharing these rows
+    const uint32_t t_lane = tmem_base + (uint32_t(rg * 32) << 16);
+    const uint32_t t_s = t_lane + TM_S + X * BKV + half * HW;
+    const uint32_t t_p = t_lane + TM_P + X * PSLOT + half * PW;
+    const uint32_t t_o = t_lane + TM_O + X * HD;
     const float c = p.scale_log2e;
-    RowState<HD> rs;
-    rs.m_ref = 0.f;
-    rs.sum = 0.f;
-    rs.t_o = t_lane + TM_O + X * HD;
-    rs.o_done = &o_done[X];
-    auto signal_s_free = [&]() {
+    float m_ref = 0.f;   // integer-valued reference in the log2 domain; identical in both warps of the pair
+    float sum = 0.f;     // partial row sum over this warp's columns
+    const bool tr = (warp & 7) == 0 && lane == 0;
+    uint32_t va[32], vt[TAILW];
+    auto load_s = [&]() {
+      tmem_ld32(t_s, va);
+      if constexpr (TAILW == 16) tmem_ld16(t_s + 32, vt);
+      else tmem_ld8(t_s + 32, vt);
+    };
+    mbar_wait(&s_full[X], 0);
+    tc_fence_after();
+    load_s();
+    for (int j = 0; j < nblk; ++j) {
+      const int ncols = min(BKV, n_keys - j * BKV);      // valid keys in this block
+      const int nv = max(0, min(HW, ncols - half * HW)); // valid columns among this warp's HW
+      const bool full = nv == HW;
+      if (tr) ATT_TRACE(1 + X, j * 6);
+      tmem_ld_wait_on(va);
+      if constexpr (TAILW == 16) tmem_ld_wait_on16(vt);
+      else tmem_ld_wait_on8(vt);
+      // S(j) is in registers: hand it back so that S(j+1) can be computed under this block's exponentials
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[X]);
-    };
-    uint32_t va[32], vb[32];
-    mbar_wait(&s_full[X], 0);
-    tc_fence_after();
-    tmem_ld32(t_s, va);
-    tmem_ld32(t_s + 32, vb);
-    for (int j = 0; j < nblk; ++j) {
-      const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
-      rs.j = j;
-      rs.sm[0] = make_float2(0.f, 0.f);
-      rs.sm[1] = make_float2(0.f, 0.f);
-      uint32_t pk[BKV / 2];
-      const bool tr = (warp & 3) == 0 && lane == 0;
-      if (tr) ATT_TRACE(1 + X, j * 6);
-      // va / vb: columns [0,32) / [32,64) of S(j), requested at the end of the previous iteration.
-      // The block is walked in chunks of 32 (16) columns; `full` blocks skip the key mask.
-#define OASR_CHUNK(BASE, W, V)                                                         \
-  do {                                                                                 \
-    if (ncols == BKV) softmax_chunk<HD, BASE, W, false, POLY>(V, ncols, c, rs, pk);    \
-    else softmax_chunk<HD, BASE, W, true, POLY>(V, ncols, c, rs, pk);                  \
-  } while (0)
-      if constexpr (BKV == 128) {
-        tmem_ld_wait_on(va);
-        tmem_ld_wait_on(vb);
-        OASR_CHUNK(0, 32, va);
-        tmem_ld32(t_s + 64, va);
-        tmem_ld_wait_on(va);
-        OASR_CHUNK(32, 32, vb);
-        tmem_ld32(t_s + 96, vb);
-        tmem_ld_wait_on(vb);
-        signal_s_free();
-        OASR_CHUNK(64, 32, va);
-        OASR_CHUNK(96, 32, vb);
-      } else if constexpr (BKV == 96) {
-        tmem_ld_wait_on(va);
-        tmem_ld_wait_on(vb);
-        if (tr) ATT_TRACE(1 + X, j * 6 + 1);
-        OASR_CHUNK(0, 32, va);
-        if (tr) ATT_TRACE(1 + X, j * 6 + 2);
-        tmem_ld32(t_s + 64, va);
-        tmem_ld_wait_on(va);
-        signal_s_free();
-        if (tr) ATT_TRACE(1 + X, j * 6 + 3);
-        OASR_CHUNK(32, 32, vb);
-        OASR_CHUNK(64, 32, va);
-        if (tr) ATT_TRACE(1 + X, j * 6 + 4);
+      if (tr) ATT_TRACE(1 + X, j * 6 + 1);
+      // row maximum of the block = max over the two halves
+      float cm = full ? fmaxf(chunk_max<32, false>(va, nv), chunk_max<TAILW, false>(vt, nv - 32))
+                      : fmaxf(chunk_max<32, true>(va, nv), chunk_max<TAILW, true>(vt, nv - 32));
+      float* xm = xch_max + (((j & 1) * 2 + X) * 2) * BQ;
+      xm[half * BQ + r] = cm;
+      named_bar_sync(pair_bar, 64);
+      cm = fmaxf(cm, xm[(half ^ 1) * BQ + r]);
+      if (tr) ATT_TRACE(1 + X, j * 6 + 2);
+      if (j == 0) {
+        m_ref = ceilf(cm * c);   // column 0 of block 0 is always a valid key
       } else {
-        static_assert(BKV == 80, "key block");
-        uint32_t vc[16];
-        tmem_ld16(t_s + 64, vc);
-        tmem_ld_wait_on(va);
-        tmem_ld_wait_on(vb);
-        tmem_ld_wait_on16(vc);
-        signal_s_free();
-        OASR_CHUNK(0, 32, va);
-        OASR_CHUNK(32, 32, vb);
-        OASR_CHUNK(64, 16, vc);
+        const float need = fmaf(cm, c, -m_ref);
+        if (__any_sync(0xffffffffu, need > REF_MARGIN)) {
+          // rare: move the reference (same decision in both warps of the pair)
+          const float k = need > REF_MARGIN ? ceilf(need) : 0.f;
+          const float f = ex2(-k);   // exact (k is an integer); 0 when the old reference was hopelessly low
+          m_ref += k;
+          sum *= f;
+          if (half == 0) {   // the lo warp rescales O; P.V(j) cannot start before both warps' p_full
+            mbar_wait(&o_done[X], (j - 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < HD; cc += 16) {
+              uint32_t v[16];
+              tmem_ld16(t_o + cc, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st16(t_o + cc, v);
+            }
+            tmem_st_wait();
+          }
+        }
       }
-#undef OASR_CHUNK
-      // S(j+1) was issued when s_free(j) arrived, i.e. long ago: request its first two chunks now so that the TMEM
-      // read latency hides under the P hand-off below
+      uint32_t pk[PW];
+      float2 sm[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 c2 = make_float2(c, c), nm2 = make_float2(-m_ref, -m_ref);
+      if (full) {
+        chunk_exp<32, 0, false>(va, nv, c2, nm2, sm, pk);
+        chunk_exp<TAILW, 16, false>(vt, nv - 32, c2, nm2, sm, pk);
+      } else {
+        chunk_exp<32, 0, true>(va, nv, c2, nm2, sm, pk);
+        chunk_exp<TAILW, 16, true>(vt, nv - 32, c2, nm2, sm, pk);
+      }
+      if (tr) ATT_TRACE(1 + X, j * 6 + 3);
+      // S(j+1) was issued when s_free(j) completed: request it now so that the TMEM read hides under the P hand-off
       if (j + 1 < nblk) {
         mbar_wait(&s_full[X], (j + 1) & 1);
         tc_fence_after();
-        tmem_ld32(t_s, va);
-        tmem_ld32(t_s + 32, vb);
+        load_s();
       }
       {
-        const float2 t = fadd2(rs.sm[0], rs.sm[1]);
-        rs.sum += t.x + t.y;
+        const float2 t = fadd2(sm[0], sm[1]);
+        sum += t.x + t.y;
       }
-      // The P buffer is free once P.V_X(j-1) has retired.  S_X(j+1) was issued after P.V_X(j-1) by the same thread and
-      // tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it; only the last
-      // block has to ask o_done (an mbarrier round trip costs ~150 cycles on this critical path).
+      // The P buffer is free once P.V_X(j-1) has retired; the s_full(j+1) wait above implies it (see v4)
       if (j > 0 && j + 1 >= nblk) {
         mbar_wait(&o_done[X], (j - 1) & 1);
         tc_fence_after();
       }
-#pragma unroll
-      for (int q4 = 0; q4 < (BKV / 2) / 16; ++q4) {
+      if (tr) ATT_TRACE(1 + X, j * 6 + 4);
+      {
         uint32_t w16[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w16[i] = pk[q4 * 16 + i];
-        tmem_st16(t_p + q4 * 16, w16);
-      }
-      if constexpr ((BKV / 2) % 16 == 8) {
-        uint32_t w8[8];
+        for (int i = 0; i < 16; ++i) w16[i] = pk[i];
+        tmem_st16(t_p, w16);
+        if constexpr (PW == 24) {
+          uint32_t w8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w8[i] = pk[(BKV / 2) - 8 + i];
-        tmem_st8(t_p + (BKV / 2) - 8, w8);
+          for (int i = 0; i < 8; ++i) w8[i] = pk[16 + i];
+          tmem_st8(t_p + 16, w8);
+        } else {
+          static_assert(PW == 20, "packed words per warp");
+          uint32_t w4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w4[i] = pk[16 + i];
+          tmem_st4(t_p + 16, w4);
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -495,17 +434,24 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       if (lane == 0) mbar_arrive(&p_full[X]);
       if (tr) ATT_TRACE(1 + X, j * 6 + 5);
     }
-    // epilogue: O / rowsum -> bf16
+    // row sum = sum of the two partial sums
+    xch_sum[(X * 2 + half) * BQ + r] = sum;
+    named_bar_sync(pair_bar, 64);
+    sum += xch_sum[(X * 2 + (half ^ 1)) * BQ + r];
+    // epilogue: O / rowsum -> bf16; the head dimension is split between the two warps in groups of 16 columns
     mbar_wait(&o_done[X], (nblk - 1) & 1);
     tc_fence_after();
-    const float inv = 1.0f / rs.sum;
+    const float inv = 1.0f / sum;
     const int qrow = q0 + X * BQ + r;
     const bool row_ok = qrow < p.T;
     __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * HD;
+    constexpr int NG = HD / 16, NG_LO = (NG + 1) / 2;
+    const int g0 = half == 0 ? 0 : NG_LO, g1 = half == 0 ? NG_LO : NG;
 #pragma unroll 1
-    for (int cc = 0; cc < HD; cc += 16) {
+    for (int g = g0; g < g1; ++g) {
+      const int cc = g * 16;
       uint32_t v[16];
-      tmem_ld16(rs.t_o + cc, v);
+      tmem_ld16(t_o + cc, v);
       tmem_ld_wait();
       if (row_ok) {
         uint32_t o[8];
@@ -521,7 +467,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   }
 
   __syncthreads();
-  if (warp == 9) {
+  if (warp == SOFTMAX_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -541,12 +487,12 @@ struct AttKey {
 struct AttMaps {
   CUtensorMap tm[6];
 };
-std::map<AttKey, AttMaps> g_att4_tmaps;
-std::mutex g_att4_mu;
+std::map<AttKey, AttMaps> g_att5_tmaps;
+std::mutex g_att5_mu;
 
 }  // namespace
 
-int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+int attention_bf16_v5(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream) {
   OASR_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "attention: bad arguments");
   OASR_REQUIRE(hd % 16 == 0 && hd >= 16 && hd <= 128, "attention: head_dim must be a multiple of 16 in [16, 128]");
@@ -556,10 +502,10 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   const int bkv = att_bkv(hd);
   AttMaps m;
   {
-    std::lock_guard<std::mutex> g(g_att4_mu);
+    std::lock_guard<std::mutex> g(g_att5_mu);
     AttKey key{qkv, B, T, 3 * d, bkv};
-    auto it = g_att4_tmaps.find(key);
-    if (it == g_att4_tmaps.end()) {
+    auto it = g_att5_tmaps.find(key);
+    if (it == g_att5_tmaps.end()) {
       uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
       uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
       const uint32_t widths[3] = {64, 32, 16};
@@ -570,19 +516,20 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
         OASR_TRY(make_tmap_bf16(&m.tm[i], qkv, 3, dims, strides, qbox, swz[i]));
         OASR_TRY(make_tmap_bf16(&m.tm[3 + i], qkv, 3, dims, strides, kbox, swz[i]));
       }
-      if (g_att4_tmaps.size() > 1024) g_att4_tmaps.clear();
-      g_att4_tmaps[key] = m;
+      if (g_att5_tmaps.size() > 1024) g_att5_tmaps.clear();
+      g_att5_tmaps[key] = m;
     } else {
       m = it->second;
     }
   }
-  Attn4Params p;
+  Attn5Params p;
   const int q_tile_bytes = BQ * hd * 2, kv_tile_bytes = bkv * hd * 2;
-  int kv_stages = (227 * 1024 - 2048 - 2 * q_tile_bytes) / (2 * kv_tile_bytes);
+  const int tail_bytes = 256 + 2 * 2 * 2 * BQ * 4 + 2 * 2 * BQ * 4;   // barriers + maximum / sum exchange
+  int kv_stages = (227 * 1024 - 1024 - tail_bytes - 2 * q_tile_bytes) / (2 * kv_tile_bytes);
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
   OASR_REQUIRE(kv_stages >= 2, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
-  const int smem_bytes = 2 * q_tile_bytes + 2 * kv_tile_bytes * kv_stages + 256 + 1024;
+  const int smem_bytes = 2 * q_tile_bytes + 2 * kv_tile_bytes * kv_stages + tail_bytes + 1024;
   p.T = T;
   p.H = H;
   p.d = d;
@@ -597,20 +544,17 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   }
   dim3 grid((T + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaError_t attr_err = cudaSuccess;
-  // POLY (share of exponentials moved to the FMA pipe): measured 587 / 613 / 580 / 568 us for POLY = 0 / 2 / 3 / 4 at the
-  // 1B shape - within run-to-run noise, the softmax warps are issue/latency-bound, not MUFU-bound - so only the plain
-  // MUFU variant is instantiated.
 #define OASR_ATT_CASE(HDV)                                                                                      \
   case HDV: {                                                                                                   \
     static bool attr_done = false;                                                                              \
     if (!attr_done) {                                                                                           \
-      attr_err = cudaFuncSetAttribute(attention_v4_kernel<HDV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      attr_err = cudaFuncSetAttribute(attention_v5_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                       227 * 1024);                                                              \
       attr_done = attr_err == cudaSuccess;                                                                      \
     }                                                                                                           \
     if (attr_err == cudaSuccess)                                                                                \
-      attention_v4_kernel<HDV, 0><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
-                                                                             m.tm[4], m.tm[5], p);              \
+      attention_v5_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3],   \
+                                                                          m.tm[4], m.tm[5], p);                 \
     break;                                                                                                      \
   }
   switch (hd) {
