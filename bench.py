@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident leg")
     ap.add_argument("--cpu-windows", type=int, default=2, help="windows in the bounded CPU sample")
+    ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree (BASELINE config 4: 7B encoder over "
+                                                      "2/4/8 GPUs); must equal --gpus, every rank sees the same batch")
     return ap.parse_args()
 
 
@@ -218,12 +220,22 @@ def run_ours(args):
     cfg = get_model_config(args.model)
     B, L = args.batch, int(WINDOW_SEC * SR)
     T = cfg.feature_length(L)
-    eng = CtcEngine(cfg, device=dev)
+    tp = args.tp
+    if tp > 1:
+        if tp != world:
+            raise ValueError("--tp must equal --gpus (one tensor-parallel group)")
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(CtcEngine.tp_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng = CtcEngine(cfg, device=dev, tp_rank=rank, tp_world=world, tp_id=idt.cpu().numpy().tobytes())
+    else:
+        eng = CtcEngine(cfg, device=dev)
     eng.load_state_dict(random_weights(cfg, 0, dev))
-    host = synthetic_windows(B, 1234 + rank).pin_memory()
+    host = synthetic_windows(B, 1234 + (0 if tp > 1 else rank)).pin_memory()
     ns = [L] * B
     wave_dev = host.to(dev)
-    audio_per_step = world * B * WINDOW_SEC
+    audio_per_step = (1 if tp > 1 else world) * B * WINDOW_SEC
 
     # ---------------------------------------------------------------- device-resident leg ("value")
     for _ in range(args.warmup):
@@ -293,7 +305,7 @@ def run_ours(args):
         "traffic": None,
         "flops_per_launch": g_flops / max(g_cnt, 1), "avg_launch_ms": g_ms / max(g_cnt, 1),
         "share_of_step": g_ms / total_stage_ms,
-        "whole_path_tflops": sum(fl.values()) * B * world * args.steps / (dev_ms / 1e3) / 1e12,
+        "whole_path_tflops": sum(fl.values()) * B * (1 if tp > 1 else world) * args.steps / (dev_ms / 1e3) / 1e12,
         "stages": stages,
     }
 
@@ -303,7 +315,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model}, {B} x 30 s synthetic 16 kHz windows per GPU (BASELINE configs[1]), "
                                "random-init weights, bf16 operands / fp32 accumulate",
-                   "windows_per_gpu": B, "frames_per_window": T, "parallelism": f"dp{world} (window shards, no collective)",
+                   "windows_per_gpu": B, "frames_per_window": T, "parallelism": (f"tp{world} (encoder split over heads / FFN columns, 2 NCCL all-reduces per layer)" if tp > 1
+                                   else f"dp{world} (window shards, no collective)"),
                    "l2": "inputs re-read from HBM every step: per-step working set (FE activations ~6 GB, encoder "
                          "activations ~1.5 GB, weights 1.9 GB) is far larger than the 126 MB L2"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

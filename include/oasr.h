@@ -88,6 +88,20 @@ OASR_API int oasr_load_weight(OasrHandle h, const char* name, const void* data, 
 /* Folds weight-norm, repacks conv filters tap-major, converts tensor-core operands to bf16. */
 OASR_API int oasr_finalize_weights(OasrHandle h);
 
+/* ---- tensor parallelism (7B encoder, BASELINE config 4; upstream has no counterpart: a replica per GPU is the
+ * default and needs none of this) --------------------------------------------------------------------------
+ * The encoder layers are split Megatron-style over `world` ranks, one process and one handle per GPU: q/k/v and
+ * FFN1 by output columns (whole heads), out-proj and FFN2 by input columns; their partial outputs are summed with
+ * one all-reduce each (NCCL over NVLink, loaded with dlopen) and added to the fp32 residual stream inside the next
+ * LayerNorm pass.  Every rank loads the FULL weights with oasr_load_weight and keeps its slice at finalize.
+ * oasr_tp_unique_id: rank 0 obtains the 128-byte NCCL id, the host broadcasts it.
+ * oasr_tp_init: collective; call after oasr_create and before oasr_finalize_weights.
+ * oasr_tp_emulate: one handle computes all `world` shards in turn and sums them locally (no communicator) - the
+ * single-GPU parity check of the slicing. */
+OASR_API int oasr_tp_unique_id(void* id_out_128_bytes);
+OASR_API int oasr_tp_init(OasrHandle h, int32_t rank, int32_t world, const void* id_128_bytes);
+OASR_API int oasr_tp_emulate(OasrHandle h, int32_t world);
+
 /* Frames produced for n_samples input samples: chain of floor((L-k)/s)+1 over the FE layers. */
 OASR_API int32_t oasr_feature_length(const OasrConfig* cfg, int64_t n_samples);
 
@@ -124,7 +138,7 @@ OASR_API int64_t oasr_launch_count(OasrHandle h);
 enum {
   OASR_PROF_WAVE_NORM = 0, OASR_PROF_FE0, OASR_PROF_FE_CONV, OASR_PROF_LAYERNORM, OASR_PROF_PROJ,
   OASR_PROF_POSCONV, OASR_PROF_QKV, OASR_PROF_ATTENTION, OASR_PROF_OUTPROJ, OASR_PROF_FFN1, OASR_PROF_FFN2,
-  OASR_PROF_CTC_HEAD, OASR_PROF_DECODE, OASR_PROF_END, OASR_PROF_NCAT
+  OASR_PROF_CTC_HEAD, OASR_PROF_DECODE, OASR_PROF_ALLREDUCE, OASR_PROF_END, OASR_PROF_NCAT
 };
 OASR_API int oasr_profile_enable(OasrHandle h, int32_t on);
 OASR_API int oasr_profile_read(OasrHandle h, double* ms, int64_t* counts, int32_t n);

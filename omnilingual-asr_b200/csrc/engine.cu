@@ -4,6 +4,7 @@
 #include "host_util.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "tp_comm.h"
 
 #include <algorithm>
 #include <cstring>
@@ -84,12 +85,26 @@ __global__ void posfold_kernel(const float* __restrict__ v, const float* __restr
   }
 }
 
+// out[r][c] = bf16(in[r][col0 + c]) for c < ncols: the input-column slice of a row-parallel weight
+__global__ void slice_cols_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long rows,
+                                       int in_ld, int col0, int ncols) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * ncols) return;
+  const long long r = i / ncols;
+  const int c = int(i - r * ncols);
+  out[i] = __float2bfloat16(in[r * in_ld + col0 + c]);
+}
+
 inline unsigned blocks_for(long long n, int threads = 256) { return (unsigned)((n + threads - 1) / threads); }
 
 struct LayerW {
   float *attn_ln_g, *attn_ln_b, *ffn_ln_g, *ffn_ln_b;
   __nv_bfloat16 *wqkv, *wo, *w1, *w2;
   float *bqkv, *bo, *b1, *b2;
+  // tensor parallelism: slices per local shard (one in a real run, `world` when emulated); bo / b2 stay whole and
+  // are added by shard 0 only
+  std::vector<__nv_bfloat16*> s_wqkv, s_wo, s_w1, s_w2;
+  std::vector<float*> s_bqkv, s_b1;
 };
 
 }  // namespace
@@ -143,6 +158,11 @@ struct OasrEngine {
   std::vector<cudaEvent_t> prof_pool;
   double prof_ms[OASR_PROF_NCAT] = {};
   int64_t prof_n[OASR_PROF_NCAT] = {};
+  // tensor parallelism (encoder layers only): this handle computes shards [tp_first, tp_first + tp_local) of tp_world
+  int tp_world = 1, tp_first = 0, tp_local = 1;
+  bool tp_emulated = false;
+  void* tp_comm = nullptr;
+  float* part = nullptr;            // [M, d] fp32 partial sums of the row-parallel GEMMs
   // shapes of the last forward (debug buffers)
   int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
   long long last_fe_pad = 0;
@@ -212,6 +232,7 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   OASR_TRY(A((void**)&e->qkv, (size_t)M * 3 * d * 2, false));
   OASR_TRY(A((void**)&e->att, (size_t)M * d * 2, false));
   OASR_TRY(A((void**)&e->ffn, (size_t)M * F * 2, false));
+  if (e->tp_world > 1) OASR_TRY(A((void**)&e->part, (size_t)M * d * 4, false));
   OASR_TRY(A((void**)&e->keys, (size_t)M * 8, true));
   OASR_TRY(A((void**)&e->n_samples_dev, (size_t)nB * 4, true));
   OASR_TRY(A((void**)&e->n_frames_dev, (size_t)nB * 4, true));
@@ -394,6 +415,93 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
 
   // a14
   const float scale = 1.0f / sqrtf((float)hd);
+  if (e->tp_world > 1) {
+    // Tensor-parallel layers: q/k/v + attention + FFN1 on this rank's heads / hidden columns, out-proj and FFN2 as
+    // partial sums over the local input columns -> all-reduce -> residual add fused into the next LayerNorm pass.
+    const int W = e->tp_world, d_loc = d / W, F_loc = F / W, H_loc = H / W;
+    auto reduce_partial = [&]() -> int {
+      if (e->tp_comm != nullptr) {
+        prof_mark(e, OASR_PROF_ALLREDUCE, st);
+        OASR_TRY(tp_allreduce_f32(e->tp_comm, e->part, (size_t)M * d, st));
+      }
+      return OASR_OK;
+    };
+    prof_mark(e, OASR_PROF_LAYERNORM, st);
+    if (c.n_layers > 0)
+      OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->layers[0].attn_ln_g, e->layers[0].attn_ln_b, e->lnbuf, nullptr, st));
+    for (int l = 0; l < c.n_layers; ++l) {
+      const LayerW& w = e->layers[l];
+      for (int s = 0; s < e->tp_local; ++s) {
+        const bool first = s == 0;   // shard 0 of the handle starts the partial sum (and rank 0 adds the bias)
+        const bool add_bias = e->tp_first + s == 0;
+        prof_mark(e, OASR_PROF_QKV, st);
+        {
+          GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.s_wqkv[s], 3 * d_loc);
+          a.bias = w.s_bqkv[s];
+          a.out = e->qkv;
+          a.ldo = 3 * d_loc;
+          a.epilogue = EPI_BF16;
+          OASR_TRY(gemm_bf16_tcgen05(a, st));
+        }
+        prof_mark(e, OASR_PROF_ATTENTION, st);
+        OASR_TRY(attention_bf16(e->qkv, e->att, e->n_frames_dev, B, T, H_loc, hd, scale, st));
+        prof_mark(e, OASR_PROF_OUTPROJ, st);
+        {
+          GemmArgs a = GemmArgs::plain(e->att, (int)M, d_loc, d_loc, w.s_wo[s], d);
+          a.bias = add_bias ? w.bo : nullptr;
+          a.out = e->part;
+          a.ldo = d;
+          a.resid = first ? nullptr : e->part;
+          a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          OASR_TRY(gemm_bf16_tcgen05(a, st));
+        }
+        e->launches += 3;
+      }
+      OASR_TRY(reduce_partial());
+      prof_mark(e, OASR_PROF_LAYERNORM, st);
+      OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.ffn_ln_g, w.ffn_ln_b, e->lnbuf, nullptr, e->part, e->x, st));
+      for (int s = 0; s < e->tp_local; ++s) {
+        const bool first = s == 0;
+        const bool add_bias = e->tp_first + s == 0;
+        prof_mark(e, OASR_PROF_FFN1, st);
+        {
+          GemmArgs a = GemmArgs::plain(e->lnbuf, (int)M, d, d, w.s_w1[s], F_loc);
+          a.bias = w.s_b1[s];
+          a.out = e->ffn;
+          a.ldo = F_loc;
+          a.epilogue = EPI_BF16_GELU;
+          OASR_TRY(gemm_bf16_tcgen05(a, st));
+        }
+        prof_mark(e, OASR_PROF_FFN2, st);
+        {
+          GemmArgs a = GemmArgs::plain(e->ffn, (int)M, F_loc, F_loc, w.s_w2[s], d);
+          a.bias = add_bias ? w.b2 : nullptr;
+          a.out = e->part;
+          a.ldo = d;
+          a.resid = first ? nullptr : e->part;
+          a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          OASR_TRY(gemm_bf16_tcgen05(a, st));
+        }
+        e->launches += 2;
+      }
+      OASR_TRY(reduce_partial());
+      // residual add + the next LayerNorm (the next layer's attention norm, or the final norm) in one pass
+      prof_mark(e, OASR_PROF_LAYERNORM, st);
+      const bool last = l + 1 == c.n_layers;
+      const float* g = last ? e->final_ln_g : e->layers[l + 1].attn_ln_g;
+      const float* bta = last ? e->final_ln_b : e->layers[l + 1].attn_ln_b;
+      OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, last ? hidden_out : nullptr, e->part, e->x, st));
+      e->launches += 2;
+      if (stop_stage == 4 + l) {
+        prof_mark(e, OASR_PROF_END, st);
+        return OASR_OK;
+      }
+    }
+    if (c.n_layers == 0) {
+      prof_mark(e, OASR_PROF_LAYERNORM, st);
+      OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
+    }
+  } else {
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerW& w = e->layers[l];
     prof_mark(e, OASR_PROF_LAYERNORM, st);
@@ -448,6 +556,7 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   }
   prof_mark(e, OASR_PROF_LAYERNORM, st);
   OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
+  }
   prof_mark(e, OASR_PROF_CTC_HEAD, st);
   // a15: logits stay in TMEM; only a packed (max, index) key per frame reaches HBM
   OASR_CUDA_CHECK(cudaMemsetAsync(e->keys, 0, (size_t)M * 8, st));
@@ -523,7 +632,45 @@ void oasr_destroy(OasrHandle h) {
   for (cudaEvent_t ev : h->stage_ev) if (ev) cudaEventDestroy(ev);
   for (auto& m : h->prof_marks) cudaEventDestroy(m.second);
   for (cudaEvent_t ev : h->prof_pool) cudaEventDestroy(ev);
+  tp_comm_destroy(h->tp_comm);
   delete h;
+}
+
+static int tp_check_split(OasrHandle h, int world) {
+  OASR_REQUIRE(h, "tensor parallelism: null handle");
+  if (h->finalized) return fail(OASR_ERR_STATE, "tensor parallelism must be set up before oasr_finalize_weights");
+  const OasrConfig& c = h->cfg;
+  OASR_REQUIRE(world >= 1 && world <= 64, "tensor parallelism: world size out of range");
+  if (c.n_heads % world != 0 || (c.d_model / world) % 64 != 0 || (c.d_ffn / world) % 64 != 0 || c.d_ffn % world != 0)
+    return fail(OASR_ERR_UNSUPPORTED, "tensor parallelism: heads must divide by the world size and d_model / world, "
+                                      "d_ffn / world must be multiples of 64");
+  return OASR_OK;
+}
+
+int oasr_tp_unique_id(void* id_out) {
+  OASR_REQUIRE(id_out, "oasr_tp_unique_id: null argument");
+  return tp_unique_id(id_out);
+}
+
+int oasr_tp_init(OasrHandle h, int32_t rank, int32_t world, const void* id) {
+  OASR_TRY(tp_check_split(h, world));
+  OASR_REQUIRE(rank >= 0 && rank < world && id, "oasr_tp_init: bad rank / id");
+  if (h->tp_comm != nullptr || h->tp_world != 1) return fail(OASR_ERR_STATE, "tensor parallelism already initialised");
+  if (world > 1) OASR_TRY(tp_comm_create(&h->tp_comm, rank, world, id));
+  h->tp_world = world;
+  h->tp_first = rank;
+  h->tp_local = 1;
+  return OASR_OK;
+}
+
+int oasr_tp_emulate(OasrHandle h, int32_t world) {
+  OASR_TRY(tp_check_split(h, world));
+  if (h->tp_comm != nullptr || h->tp_world != 1) return fail(OASR_ERR_STATE, "tensor parallelism already initialised");
+  h->tp_world = world;
+  h->tp_first = 0;
+  h->tp_local = world;
+  h->tp_emulated = true;
+  return OASR_OK;
 }
 
 int oasr_load_weight(OasrHandle h, const char* name, const void* data, int dtype, const int64_t* shape, int ndim) {
@@ -651,17 +798,51 @@ int oasr_finalize_weights(OasrHandle h) {
     OASR_TRY(get_raw(e, p + "ffn2.weight", {d, F}, &w2));
     OASR_TRY(get_raw(e, p + "ffn2.bias", {d}, &w.b2));
     const long long dd = (long long)d * d;
-    OASR_TRY(alloc_owned(e, (void**)&w.wqkv, (size_t)dd * 3 * 2));
-    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wq, w.wqkv, dd);
-    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wk, w.wqkv + dd, dd);
-    cast_bf16_kernel<<<blocks_for(dd), 256>>>(wv, w.wqkv + 2 * dd, dd);
-    OASR_TRY(alloc_owned(e, (void**)&w.bqkv, (size_t)d * 3 * 4));
-    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv, bq, (size_t)d * 4, cudaMemcpyDeviceToDevice));
-    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + d, bk, (size_t)d * 4, cudaMemcpyDeviceToDevice));
-    OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + 2 * d, bv, (size_t)d * 4, cudaMemcpyDeviceToDevice));
-    OASR_TRY(to_bf16(e, wo, dd, &w.wo));
-    OASR_TRY(to_bf16(e, w1, (long long)F * d, &w.w1));
-    OASR_TRY(to_bf16(e, w2, (long long)F * d, &w.w2));
+    if (e->tp_world == 1) {
+      OASR_TRY(alloc_owned(e, (void**)&w.wqkv, (size_t)dd * 3 * 2));
+      cast_bf16_kernel<<<blocks_for(dd), 256>>>(wq, w.wqkv, dd);
+      cast_bf16_kernel<<<blocks_for(dd), 256>>>(wk, w.wqkv + dd, dd);
+      cast_bf16_kernel<<<blocks_for(dd), 256>>>(wv, w.wqkv + 2 * dd, dd);
+      OASR_TRY(alloc_owned(e, (void**)&w.bqkv, (size_t)d * 3 * 4));
+      OASR_CUDA_CHECK(cudaMemcpy(w.bqkv, bq, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+      OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + d, bk, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+      OASR_CUDA_CHECK(cudaMemcpy(w.bqkv + 2 * d, bv, (size_t)d * 4, cudaMemcpyDeviceToDevice));
+    }
+    if (e->tp_world == 1) {
+      OASR_TRY(to_bf16(e, wo, dd, &w.wo));
+      OASR_TRY(to_bf16(e, w1, (long long)F * d, &w.w1));
+      OASR_TRY(to_bf16(e, w2, (long long)F * d, &w.w2));
+    } else {
+      const int W = e->tp_world, d_loc = d / W, F_loc = F / W;
+      for (int s = 0; s < e->tp_local; ++s) {
+        const int r = e->tp_first + s;
+        __nv_bfloat16 *sq = nullptr, *so = nullptr, *s1 = nullptr, *s2 = nullptr;
+        float *sbq = nullptr, *sb1 = nullptr;
+        // q | k | v rows of this shard's heads
+        const long long blk = (long long)d_loc * d;
+        OASR_TRY(alloc_owned(e, (void**)&sq, (size_t)blk * 3 * 2));
+        cast_bf16_kernel<<<blocks_for(blk), 256>>>(wq + (long long)r * blk, sq, blk);
+        cast_bf16_kernel<<<blocks_for(blk), 256>>>(wk + (long long)r * blk, sq + blk, blk);
+        cast_bf16_kernel<<<blocks_for(blk), 256>>>(wv + (long long)r * blk, sq + 2 * blk, blk);
+        OASR_TRY(alloc_owned(e, (void**)&sbq, (size_t)d_loc * 3 * 4));
+        OASR_CUDA_CHECK(cudaMemcpy(sbq, bq + r * d_loc, (size_t)d_loc * 4, cudaMemcpyDeviceToDevice));
+        OASR_CUDA_CHECK(cudaMemcpy(sbq + d_loc, bk + r * d_loc, (size_t)d_loc * 4, cudaMemcpyDeviceToDevice));
+        OASR_CUDA_CHECK(cudaMemcpy(sbq + 2 * d_loc, bv + r * d_loc, (size_t)d_loc * 4, cudaMemcpyDeviceToDevice));
+        // out-proj: input columns of this shard's heads
+        OASR_TRY(alloc_owned(e, (void**)&so, (size_t)d * d_loc * 2));
+        slice_cols_bf16_kernel<<<blocks_for((long long)d * d_loc), 256>>>(wo, so, d, d, r * d_loc, d_loc);
+        // FFN1: rows, FFN2: input columns
+        OASR_TRY(alloc_owned(e, (void**)&s1, (size_t)F_loc * d * 2));
+        cast_bf16_kernel<<<blocks_for((long long)F_loc * d), 256>>>(w1 + (long long)r * F_loc * d, s1, (long long)F_loc * d);
+        OASR_TRY(alloc_owned(e, (void**)&sb1, (size_t)F_loc * 4));
+        OASR_CUDA_CHECK(cudaMemcpy(sb1, w.b1 + r * F_loc, (size_t)F_loc * 4, cudaMemcpyDeviceToDevice));
+        OASR_TRY(alloc_owned(e, (void**)&s2, (size_t)d * F_loc * 2));
+        slice_cols_bf16_kernel<<<blocks_for((long long)d * F_loc), 256>>>(w2, s2, d, F, r * F_loc, F_loc);
+        OASR_CUDA_CHECK(cudaGetLastError());
+        w.s_wqkv.push_back(sq); w.s_wo.push_back(so); w.s_w1.push_back(s1); w.s_w2.push_back(s2);
+        w.s_bqkv.push_back(sbq); w.s_b1.push_back(sb1);
+      }
+    }
     OASR_CUDA_CHECK(cudaDeviceSynchronize());
     for (const char* n : {"q.weight", "k.weight", "v.weight", "o.weight", "ffn1.weight", "ffn2.weight"}) free_raw(e, p + n);
   }

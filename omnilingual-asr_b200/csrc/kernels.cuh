@@ -22,6 +22,12 @@ int fe_layer0(const float* wave, long long in_stride, int B, int L, const float*
 int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
                    const float* gamma, const float* beta, void* out_bf16, float* out_f32, cudaStream_t stream);
 
+// Tensor-parallel residual + LayerNorm in one pass: row = in + add (fp32, contiguous rows), written to sum_out (may
+// alias in), LayerNorm(row) -> out_bf16 / out_f32.
+int add_layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
+                       const float* gamma, const float* beta, void* out_bf16, float* out_f32, const float* add,
+                       float* sum_out, cudaStream_t stream);
+
 // x fp32 [B*T, d] -> bf16 copy with `pad` zero rows before and after every sequence: [B, T + 2*pad, d]
 // (only the T middle rows are written; the caller zeroes the buffer once).
 int pad_cast_bf16(const float* x, int B, int T, int d, int pad, void* out_bf16, cudaStream_t stream);

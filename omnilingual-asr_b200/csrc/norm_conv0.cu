@@ -179,9 +179,9 @@ fe_layer0_kernel(const float* __restrict__ wave, long long in_stride, int T0, co
 // four 256-thread blocks per SM; the kernel is HBM-bound and needs the loads of many rows in flight.
 template <bool IN_BF16, int MAXJ>
 __global__ void __launch_bounds__(256, MAXJ <= 10 ? 3 : 2)
-layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int batches, int rows_per_batch, int D,
+layernorm_kernel(const void* in, long long in_batch_stride, int batches, int rows_per_batch, int D,
                  const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out_bf16,
-                 float* __restrict__ out_f32) {
+                 float* __restrict__ out_f32, const float* __restrict__ add, float* sum_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   const long long total = (long long)batches * rows_per_batch;
@@ -212,7 +212,12 @@ layernorm_kernel(const void* __restrict__ in, long long in_batch_stride, int bat
     for (int j = 0; j < MAXJ; ++j) {
       const int g = lane + 32 * j;
       if (g < ngroups) {
-        v[j] = __ldg(p + g);
+        v[j] = p[g];
+        if (add != nullptr) {   // tensor-parallel residual: row = in + add, written back to sum_out (may alias in)
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(add + row * D) + g);
+          v[j].x += a4.x; v[j].y += a4.y; v[j].z += a4.z; v[j].w += a4.w;
+          reinterpret_cast<float4*>(sum_out + row * D)[g] = v[j];
+        }
         s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
       }
     }
@@ -301,7 +306,16 @@ int fe_layer0(const float* wave, long long in_stride, int B, int L, const float*
 
 int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
                    const float* gamma, const float* beta, void* out_bf16, float* out_f32, cudaStream_t stream) {
+  return add_layernorm_rows(in, in_is_bf16, in_batch_stride, batches, rows_per_batch, D, gamma, beta, out_bf16, out_f32,
+                            nullptr, nullptr, stream);
+}
+
+int add_layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, int batches, int rows_per_batch, int D,
+                       const float* gamma, const float* beta, void* out_bf16, float* out_f32, const float* add,
+                       float* sum_out, cudaStream_t stream) {
   OASR_REQUIRE(in && gamma && beta && (out_bf16 || out_f32), "layernorm: bad arguments");
+  OASR_REQUIRE(add == nullptr || (!in_is_bf16 && sum_out != nullptr && in_batch_stride == 0 && batches == 1),
+               "layernorm: the add variant takes contiguous fp32 rows");
   OASR_REQUIRE(D % 4 == 0 && D <= 2048 && D > 0, "layernorm: D must be a multiple of 4 and <= 2048");
   const long long total = (long long)batches * rows_per_batch;
   if (total == 0) return OASR_OK;
@@ -309,7 +323,7 @@ int layernorm_rows(const void* in, int in_is_bf16, long long in_batch_stride, in
   const unsigned grid = (unsigned)((total + rows_per_block - 1) / rows_per_block);
 #define OASR_LN_LAUNCH(BF, MJ)                                                                                  \
   layernorm_kernel<BF, MJ><<<grid, 256, 0, stream>>>(in, in_batch_stride, batches, rows_per_batch, D, gamma, beta,   \
-                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32)
+                                                     reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, add, sum_out)
   if (in_is_bf16) {
     if (D <= 512) OASR_LN_LAUNCH(true, 4);
     else if (D <= 1280) OASR_LN_LAUNCH(true, 10);

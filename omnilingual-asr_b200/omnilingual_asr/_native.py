@@ -18,7 +18,7 @@ DTYPE_F32, DTYPE_BF16 = 0, 1
 EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_ARGMAX, EPI_LN_GELU_BF16, EPI_F32_GELU_RESID = range(7)
 FLAG_INPUT_NORMALISED = 1
 PROF_CATEGORIES = ("wave_norm", "fe_layer0", "fe_conv_1_6", "layernorm", "feature_proj", "posconv", "qkv_gemm",
-                   "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "ctc_head_argmax", "decode", "end")
+                   "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "ctc_head_argmax", "decode", "tp_allreduce", "end")
 
 
 class OasrConfig(C.Structure):
@@ -39,6 +39,9 @@ _PROTOTYPES = {
     "oasr_destroy": (None, [_vp]),
     "oasr_load_weight": (C.c_int, [_vp, C.c_char_p, _vp, C.c_int, C.POINTER(_i64), C.c_int]),
     "oasr_finalize_weights": (C.c_int, [_vp]),
+    "oasr_tp_unique_id": (C.c_int, [_vp]),
+    "oasr_tp_init": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "oasr_tp_emulate": (C.c_int, [_vp, _i32]),
     "oasr_feature_length": (_i32, [C.POINTER(OasrConfig), _i64]),
     "oasr_forward_ctc": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_transcribe_host": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -46,7 +46,11 @@ def _as_config_struct(cfg: CtcModelConfig) -> N.OasrConfig:
 class CtcEngine:
     """One CUDA engine: weights resident in HBM, forward = a8..a16 on the calling thread's stream."""
 
-    def __init__(self, model: str | CtcModelConfig, device: Optional[torch.device | str | int] = None):
+    def __init__(self, model: str | CtcModelConfig, device: Optional[torch.device | str | int] = None, *,
+                 tp_rank: int = 0, tp_world: int = 1, tp_id: Optional[bytes] = None, tp_emulate: int = 0):
+        """tp_world > 1: this engine is rank `tp_rank` of a tensor-parallel group (one process per GPU; `tp_id` is the
+        128-byte id from `CtcEngine.tp_unique_id()` of rank 0, broadcast by the caller).  tp_emulate = W computes all
+        W shards on this one GPU and sums them locally (parity check of the slicing, no communicator)."""
         self.cfg = get_model_config(model)
         self._lib = N.load()  # raises when liboasr.so is missing: no CPU fallback
         if not torch.cuda.is_available():
@@ -60,6 +64,22 @@ class CtcEngine:
         self._finalized = False
         with torch.cuda.device(self.device):
             N.check(self._lib.oasr_create(C.byref(self._cstruct), C.byref(self._handle)), "oasr_create")
+            if tp_emulate and tp_emulate > 1:
+                N.check(self._lib.oasr_tp_emulate(self._handle, int(tp_emulate)), "oasr_tp_emulate")
+            elif tp_world > 1:
+                if tp_id is None or len(tp_id) != 128:
+                    raise ValueError("tensor parallelism needs the 128-byte id of rank 0 (CtcEngine.tp_unique_id())")
+                buf = C.create_string_buffer(bytes(tp_id), 128)
+                N.check(self._lib.oasr_tp_init(self._handle, int(tp_rank), int(tp_world), C.cast(buf, C.c_void_p)),
+                        "oasr_tp_init")
+        self.tp_world = int(tp_emulate) if tp_emulate and tp_emulate > 1 else int(tp_world)
+
+    @staticmethod
+    def tp_unique_id() -> bytes:
+        """128-byte NCCL id for a tensor-parallel group; rank 0 creates it, the caller broadcasts it."""
+        buf = C.create_string_buffer(128)
+        N.check(N.load().oasr_tp_unique_id(C.cast(buf, C.c_void_p)), "oasr_tp_unique_id")
+        return buf.raw
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, weights: Mapping[str, torch.Tensor | np.ndarray], finalize: bool = True) -> None:

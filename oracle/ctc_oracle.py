@@ -87,6 +87,8 @@ PRESETS: Dict[str, CtcModelConfig] = {
     # Small shapes for fast parity tests; same graph, legal tensor-core shapes.
     "tiny": CtcModelConfig("tiny", 256, 2, 4, 512, vocab=300),
     "tiny80": CtcModelConfig("tiny80", 320, 2, 4, 640, vocab=500, pos_groups=4),   # head_dim 80, group width 80 (1B-like)
+    # 3B / 7B widths (d 2048, head_dim 128, FFN 8192, group width 128) with two layers: the shapes of configs 3 and 4
+    "wide2l": CtcModelConfig("wide2l", 2048, 2, 16, 8192, vocab=9812),
 }
 
 PUBLISHED_PARAM_COUNTS = {

@@ -1,0 +1,52 @@
+"""Tensor-parallel parity over NCCL: every rank runs its slice of the encoder, rank 0 compares with an unsplit engine.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_check.py [preset]"""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "omnilingual-asr_b200"))
+from omnilingual_asr.models.config import CtcModelConfig  # noqa: E402
+from omnilingual_asr.models.inference.ctc_engine import CtcEngine  # noqa: E402
+from oracle import ctc_oracle as O  # noqa: E402
+from tests.golden.make_golden import golden_inputs  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+name = sys.argv[1] if len(sys.argv) > 1 else "wide2l"
+ocfg = O.PRESETS[name]
+cfg = CtcModelConfig(ocfg.name, ocfg.d_model, ocfg.n_layers, ocfg.n_heads, ocfg.d_ffn, vocab=ocfg.vocab, pos_groups=ocfg.pos_groups)
+w = O.init_weights(ocfg, seed=0)
+wave, ns = golden_inputs()
+
+idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+if rank == 0:
+    idt.copy_(torch.frombuffer(bytearray(CtcEngine.tp_unique_id()), dtype=torch.uint8))
+dist.broadcast(idt, 0)
+eng = CtcEngine(cfg, device=dev, tp_rank=rank, tp_world=world, tp_id=bytes(idt.cpu().numpy().tobytes()))
+eng.load_state_dict(w)
+res = eng.forward(wave.to(dev), ns, normalised=True, return_hidden=True)
+torch.cuda.synchronize()
+# every rank holds the same replicated result
+ids = torch.from_numpy(res.frame_ids.astype(np.int64)).to(dev)
+ids0 = ids.clone()
+dist.broadcast(ids0, 0)
+assert bool((ids == ids0).all()), "ranks disagree on the frame ids"
+if rank == 0:
+    ref = CtcEngine(cfg, device=dev)
+    ref.load_state_dict(w)
+    r0 = ref.forward(wave.to(dev), ns, normalised=True, return_hidden=True)
+    err = max(float((res.hidden[b, :nf] - r0.hidden[b, :nf]).norm() / r0.hidden[b, :nf].norm()) for b, nf in enumerate(r0.n_frames))
+    same = float(np.mean([np.mean(res.frame_ids[b, :nf] == r0.frame_ids[b, :nf]) for b, nf in enumerate(r0.n_frames)]))
+    print(f"tp{world} {name}: hidden rel err vs unsplit {err:.2e}, frame-id agreement {same:.4f}")
+    assert err < 5e-3 and same >= 0.97
+    print("TP OK")
+dist.barrier()
+dist.destroy_process_group()

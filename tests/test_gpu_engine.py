@@ -190,3 +190,55 @@ def test_batch_invariance_and_determinism_full_window(device):
     single = eng.forward(wd[1:2].contiguous(), [ns[1]])
     assert (single.frame_ids[0] == a.frame_ids[1]).all()
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------- configs 3 / 4
+def test_wide_3b_7b_shapes_two_layers(device):
+    """d_model 2048, head_dim 128, FFN 8192, pos-conv group width 128, vocabulary 9812: the widths of omniASR_CTC_3B
+    and _7B (BASELINE configs 3 and 4) on two layers, against the oracle."""
+    ocfg, w, eng = make_engine("wide2l", device)
+    wave, ns = golden_inputs()
+    res = eng.forward(wave.to(device), ns, normalised=True, return_hidden=True)
+    emu = O.forward(w, wave, ns, ocfg, emulate_bf16=True, return_logits=True)
+    hid = res.hidden.cpu()
+    for b, nf in enumerate(emu.n_frames):
+        assert rel_err(hid[b, :nf], emu.hidden[b, :nf]) < 8e-3
+    a_emu, a_emu_m, excl = agreement(res.frame_ids, emu, NEAR_TIE)
+    print(f"wide2l: agreement emu={a_emu:.4f} emu(margin>{NEAR_TIE})={a_emu_m:.4f} excluded={excl}")
+    assert a_emu_m == 1.0
+    eng.close()
+
+
+@pytest.mark.parametrize("name,world", [("tiny", 2), ("tiny", 4), ("wide2l", 8)])
+def test_tensor_parallel_slicing_emulated_on_one_gpu(device, name, world):
+    """Config 4's Megatron split (q/k/v + FFN1 by output columns, out-proj + FFN2 by input columns, partial sums added
+    to the fp32 residual stream inside the next LayerNorm pass) with all `world` shards computed by ONE handle and
+    summed locally: same kernels and slices as the multi-GPU run minus the NCCL all-reduce (tests/test_tp_multi_gpu.py
+    covers that on >= 2 GPUs).  Must agree with the unsplit engine up to fp32 summation order."""
+    ocfg = O.PRESETS[name]
+    w = O.init_weights(ocfg, seed=0)
+    wave, ns = golden_inputs()
+    ref = CtcEngine(product_cfg(ocfg), device=device)
+    ref.load_state_dict(w)
+    r0 = ref.forward(wave.to(device), ns, normalised=True, return_hidden=True)
+    ref.close()
+    tp = CtcEngine(product_cfg(ocfg), device=device, tp_emulate=world)
+    tp.load_state_dict(w)
+    r1 = tp.forward(wave.to(device), ns, normalised=True, return_hidden=True)
+    for b, nf in enumerate(r0.n_frames):
+        assert rel_err(r1.hidden[b, :nf], r0.hidden[b, :nf]) < 5e-3    # bf16 rounding chains, different fp32 sum order
+    same = float(np.mean([np.mean(r1.frame_ids[b, :nf] == r0.frame_ids[b, :nf]) for b, nf in enumerate(r0.n_frames)]))
+    print(f"tp emulate {name} x{world}: frame-id agreement with the unsplit engine {same:.4f}")
+    assert same >= 0.97
+    emu = O.forward(w, wave, ns, ocfg, emulate_bf16=True, return_logits=True)
+    _, a_m, _ = agreement(r1.frame_ids, emu, NEAR_TIE)
+    assert a_m == 1.0
+    tp.close()
+
+
+def test_tensor_parallel_rejects_bad_splits(device):
+    ocfg = O.PRESETS["tiny80"]     # 4 heads, d 320: 320 / 2 = 160 is not a multiple of 64
+    with pytest.raises(ValueError):
+        CtcEngine(product_cfg(ocfg), device=device, tp_emulate=2)
+    with pytest.raises(ValueError):
+        CtcEngine(product_cfg(O.PRESETS["tiny"]), device=device, tp_emulate=3)
