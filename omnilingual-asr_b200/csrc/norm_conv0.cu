@@ -211,16 +211,25 @@ layernorm_kernel(const void* in, long long in_batch_stride, int batches, int row
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       const int g = lane + 32 * j;
-      if (g < ngroups) {
-        v[j] = p[g];
-        if (add != nullptr) {   // tensor-parallel residual: row = in + add, written back to sum_out (may alias in)
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(add + row * D) + g);
-          v[j].x += a4.x; v[j].y += a4.y; v[j].z += a4.z; v[j].w += a4.w;
-          reinterpret_cast<float4*>(sum_out + row * D)[g] = v[j];
-        }
-        s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-      }
+      if (g < ngroups) v[j] = p[g];
     }
+    if (add != nullptr) {   // tensor-parallel residual: row = in + add, written back to sum_out (may alias in)
+      // all loads of the row are issued before the first store: sum_out may alias in, and a store inside the load
+      // loop would order every later load behind it
+      float4 a4[MAXJ];
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j)
+        if (lane + 32 * j < ngroups) a4[j] = __ldg(reinterpret_cast<const float4*>(add + row * D) + lane + 32 * j);
+#pragma unroll
+      for (int j = 0; j < MAXJ; ++j)
+        if (lane + 32 * j < ngroups) {
+          v[j].x += a4[j].x; v[j].y += a4[j].y; v[j].z += a4[j].z; v[j].w += a4[j].w;
+          reinterpret_cast<float4*>(sum_out + row * D)[lane + 32 * j] = v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (lane + 32 * j < ngroups) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   }
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
