@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident leg")
     ap.add_argument("--cpu-windows", type=int, default=2, help="windows in the bounded CPU sample")
+    ap.add_argument("--tp-mode", default="fused", choices=["fused", "nccl"],
+                    help="fused: all-reduce + residual + LayerNorm as one kernel over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree (BASELINE config 4: 7B encoder over "
                                                       "2/4/8 GPUs); must equal --gpus, every rank sees the same batch")
     return ap.parse_args()
@@ -229,6 +231,8 @@ def run_ours(args):
             idt.copy_(torch.frombuffer(bytearray(CtcEngine.tp_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         eng = CtcEngine(cfg, device=dev, tp_rank=rank, tp_world=world, tp_id=idt.cpu().numpy().tobytes())
+        if args.tp_mode == "fused":
+            eng.tp_enable_peer_memory(B, L)
     else:
         eng = CtcEngine(cfg, device=dev)
     eng.load_state_dict(random_weights(cfg, 0, dev))
@@ -315,7 +319,9 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.model}, {B} x 30 s synthetic 16 kHz windows per GPU (BASELINE configs[1]), "
                                "random-init weights, bf16 operands / fp32 accumulate",
-                   "windows_per_gpu": B, "frames_per_window": T, "parallelism": (f"tp{world} (encoder split over heads / FFN columns, 2 NCCL all-reduces per layer)" if tp > 1
+                   "windows_per_gpu": B, "frames_per_window": T, "parallelism": (f"tp{world} (encoder split over heads / FFN columns; per row-parallel GEMM "
+                                    + ("one fused reduce + residual + LayerNorm kernel over NVLink peer memory)"
+                                       if args.tp_mode == "fused" else "one NCCL all-reduce)") if tp > 1
                                    else f"dp{world} (window shards, no collective)"),
                    "l2": "inputs re-read from HBM every step: per-step working set (FE activations ~6 GB, encoder "
                          "activations ~1.5 GB, weights 1.9 GB) is far larger than the 126 MB L2"},

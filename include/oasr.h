@@ -101,6 +101,13 @@ OASR_API int oasr_finalize_weights(OasrHandle h);
 OASR_API int oasr_tp_unique_id(void* id_out_128_bytes);
 OASR_API int oasr_tp_init(OasrHandle h, int32_t rank, int32_t world, const void* id_128_bytes);
 OASR_API int oasr_tp_emulate(OasrHandle h, int32_t world);
+/* Peer-memory path (optional, after oasr_tp_init and before the first forward): the all-reduce, the residual add
+ * and the LayerNorm of every row-parallel GEMM run as ONE kernel that reads the peers' partial sums and writes x and
+ * LN(x) into every rank's buffers over NVLink (CUDA IPC mappings), instead of ncclAllReduce + a LayerNorm pass.
+ * export: allocates this rank's arena for batches up to (B, L) and returns its 64-byte cudaIpcMemHandle_t;
+ * import: takes the `world` handles in rank order (the host all-gathers them) and maps the peers. */
+OASR_API int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out_64_bytes);
+OASR_API int oasr_tp_ipc_import(OasrHandle h, const void* handles_world_x_64_bytes);
 
 /* Frames produced for n_samples input samples: chain of floor((L-k)/s)+1 over the FE layers. */
 OASR_API int32_t oasr_feature_length(const OasrConfig* cfg, int64_t n_samples);

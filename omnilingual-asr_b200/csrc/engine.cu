@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tp_comm.h"
+#include "tp_fused.h"
 
 #include <algorithm>
 #include <cstring>
@@ -163,6 +164,13 @@ struct OasrEngine {
   bool tp_emulated = false;
   void* tp_comm = nullptr;
   float* part = nullptr;            // [M, d] fp32 partial sums of the row-parallel GEMMs
+  // peer-memory path (tp_fused.cu): x | ln | part | flags of this rank live in one IPC-exported arena
+  void* tp_arena = nullptr;
+  size_t tp_off_ln = 0, tp_off_part = 0, tp_off_flags = 0, tp_x_bytes = 0;
+  std::vector<void*> tp_peer_base;  // [world], own arena at [rank]
+  TpPeerView tp_view{};
+  bool tp_fused = false;
+  unsigned long long tp_epoch = 0;
   // shapes of the last forward (debug buffers)
   int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
   long long last_fe_pad = 0;
@@ -226,13 +234,21 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   OASR_TRY(A((void**)&e->wave_partials, (size_t)nB * WAVE_NORM_SLICES * 2 * 8, false));
   OASR_TRY(A((void**)&e->fe_buf[0], (size_t)nB * fe_pad_rows((int)T0) * 512 * 2, true));
   OASR_TRY(A((void**)&e->fe_buf[1], (size_t)nB * fe_pad_rows((int)T1) * 512 * 2, true));
-  OASR_TRY(A((void**)&e->lnbuf, (size_t)M * std::max(512, d) * 2, false));
-  OASR_TRY(A((void**)&e->x, (size_t)M * d * 4, false));
+  if (e->tp_arena != nullptr) {
+    if ((size_t)M * d * 4 > e->tp_x_bytes)
+      return fail(OASR_ERR_INVALID, "batch exceeds the (B, L) the tensor-parallel peer arena was exported for");
+    e->x = reinterpret_cast<float*>(e->tp_arena);
+    e->lnbuf = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(e->tp_arena) + e->tp_off_ln);
+  } else {
+    OASR_TRY(A((void**)&e->lnbuf, (size_t)M * std::max(512, d) * 2, false));
+    OASR_TRY(A((void**)&e->x, (size_t)M * d * 4, false));
+  }
   OASR_TRY(A((void**)&e->xpad, (size_t)nB * (T + c.pos_kernel) * d * 2, true));
   OASR_TRY(A((void**)&e->qkv, (size_t)M * 3 * d * 2, false));
   OASR_TRY(A((void**)&e->att, (size_t)M * d * 2, false));
   OASR_TRY(A((void**)&e->ffn, (size_t)M * F * 2, false));
-  if (e->tp_world > 1) OASR_TRY(A((void**)&e->part, (size_t)M * d * 4, false));
+  if (e->tp_arena != nullptr) e->part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(e->tp_arena) + e->tp_off_part);
+  else if (e->tp_world > 1) OASR_TRY(A((void**)&e->part, (size_t)M * d * 4, false));
   OASR_TRY(A((void**)&e->keys, (size_t)M * 8, true));
   OASR_TRY(A((void**)&e->n_samples_dev, (size_t)nB * 4, true));
   OASR_TRY(A((void**)&e->n_frames_dev, (size_t)nB * 4, true));
@@ -457,9 +473,14 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
         }
         e->launches += 3;
       }
-      OASR_TRY(reduce_partial());
-      prof_mark(e, OASR_PROF_LAYERNORM, st);
-      OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.ffn_ln_g, w.ffn_ln_b, e->lnbuf, nullptr, e->part, e->x, st));
+      if (e->tp_fused) {   // all-reduce + residual + LayerNorm + redistribution in one kernel over peer memory
+        prof_mark(e, OASR_PROF_ALLREDUCE, st);
+        OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, w.ffn_ln_g, w.ffn_ln_b, ++e->tp_epoch, false, st));
+      } else {
+        OASR_TRY(reduce_partial());
+        prof_mark(e, OASR_PROF_LAYERNORM, st);
+        OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, w.ffn_ln_g, w.ffn_ln_b, e->lnbuf, nullptr, e->part, e->x, st));
+      }
       for (int s = 0; s < e->tp_local; ++s) {
         const bool first = s == 0;
         const bool add_bias = e->tp_first + s == 0;
@@ -484,13 +505,23 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
         }
         e->launches += 2;
       }
-      OASR_TRY(reduce_partial());
       // residual add + the next LayerNorm (the next layer's attention norm, or the final norm) in one pass
-      prof_mark(e, OASR_PROF_LAYERNORM, st);
       const bool last = l + 1 == c.n_layers;
       const float* g = last ? e->final_ln_g : e->layers[l + 1].attn_ln_g;
       const float* bta = last ? e->final_ln_b : e->layers[l + 1].attn_ln_b;
-      OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, last ? hidden_out : nullptr, e->part, e->x, st));
+      if (e->tp_fused) {
+        prof_mark(e, OASR_PROF_ALLREDUCE, st);
+        const bool want_hidden = last && hidden_out != nullptr;   // parity runs: the fp32 LayerNorm output of all rows
+        OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, g, bta, ++e->tp_epoch, want_hidden, st));
+        if (want_hidden) {
+          prof_mark(e, OASR_PROF_LAYERNORM, st);
+          OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, hidden_out, st));
+        }
+      } else {
+        OASR_TRY(reduce_partial());
+        prof_mark(e, OASR_PROF_LAYERNORM, st);
+        OASR_TRY(add_layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, last ? hidden_out : nullptr, e->part, e->x, st));
+      }
       e->launches += 2;
       if (stop_stage == 4 + l) {
         prof_mark(e, OASR_PROF_END, st);
@@ -633,6 +664,9 @@ void oasr_destroy(OasrHandle h) {
   for (auto& m : h->prof_marks) cudaEventDestroy(m.second);
   for (cudaEvent_t ev : h->prof_pool) cudaEventDestroy(ev);
   tp_comm_destroy(h->tp_comm);
+  for (size_t q = 0; q < h->tp_peer_base.size(); ++q)
+    if ((int)q != h->tp_first && h->tp_peer_base[q]) cudaIpcCloseMemHandle(h->tp_peer_base[q]);
+  if (h->tp_arena) cudaFree(h->tp_arena);
   delete h;
 }
 
@@ -670,6 +704,61 @@ int oasr_tp_emulate(OasrHandle h, int32_t world) {
   h->tp_first = 0;
   h->tp_local = world;
   h->tp_emulated = true;
+  return OASR_OK;
+}
+
+int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out) {
+  OASR_REQUIRE(h && handle_out && B > 0 && L > 0, "oasr_tp_ipc_export: bad arguments");
+  if (h->tp_world < 2 || h->tp_emulated || h->tp_comm == nullptr)
+    return fail(OASR_ERR_STATE, "oasr_tp_ipc_export needs an initialised tensor-parallel group (oasr_tp_init)");
+  if (h->tp_world > TP_MAX_WORLD) return fail(OASR_ERR_UNSUPPORTED, "peer-memory path supports at most 8 ranks");
+  if (h->tp_arena != nullptr || h->ws_B != 0) return fail(OASR_ERR_STATE, "peer arena must be exported once, before the first forward");
+  const OasrConfig& c = h->cfg;
+  const long long T = std::max(1, fe_len(c, L, c.n_fe_layers));
+  const size_t M = (size_t)B * T, d = (size_t)c.d_model;
+  auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+  h->tp_x_bytes = M * d * 4;
+  h->tp_off_ln = up(h->tp_x_bytes);
+  h->tp_off_part = h->tp_off_ln + up(M * std::max<size_t>(512, d) * 2);
+  h->tp_off_flags = h->tp_off_part + up(M * d * 4);
+  const size_t total = h->tp_off_flags + 256;
+  OASR_TRY(dev_alloc(&h->tp_arena, total, true));
+  OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t mh;
+  OASR_CUDA_CHECK(cudaIpcGetMemHandle(&mh, h->tp_arena));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &mh, sizeof(mh));
+  return OASR_OK;
+}
+
+int oasr_tp_ipc_import(OasrHandle h, const void* handles) {
+  OASR_REQUIRE(h && handles, "oasr_tp_ipc_import: bad arguments");
+  if (h->tp_arena == nullptr) return fail(OASR_ERR_STATE, "call oasr_tp_ipc_export first");
+  if (h->tp_fused) return OASR_OK;
+  const int W = h->tp_world, r = h->tp_first;
+  h->tp_peer_base.assign(W, nullptr);
+  for (int q = 0; q < W; ++q) {
+    if (q == r) {
+      h->tp_peer_base[q] = h->tp_arena;
+      continue;
+    }
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, reinterpret_cast<const uint8_t*>(handles) + (size_t)q * 64, 64);
+    OASR_CUDA_CHECK(cudaIpcOpenMemHandle(&h->tp_peer_base[q], mh, cudaIpcMemLazyEnablePeerAccess));
+  }
+  TpPeerView& v = h->tp_view;
+  v.rank = r;
+  v.world = W;
+  for (int q = 0; q < W; ++q) {
+    uint8_t* base = reinterpret_cast<uint8_t*>(h->tp_peer_base[q]);
+    v.x[q] = reinterpret_cast<float*>(base);
+    v.ln[q] = reinterpret_cast<__nv_bfloat16*>(base + h->tp_off_ln);
+    v.part[q] = reinterpret_cast<const float*>(base + h->tp_off_part);
+    v.ready[q] = reinterpret_cast<unsigned long long*>(base + h->tp_off_flags);
+    v.done[q] = v.ready[q] + TP_MAX_WORLD;
+  }
+  v.cta_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(h->tp_arena) + h->tp_off_flags + 2 * TP_MAX_WORLD * 8);
+  h->tp_fused = true;
   return OASR_OK;
 }
 

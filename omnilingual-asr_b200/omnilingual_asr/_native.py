@@ -42,6 +42,8 @@ _PROTOTYPES = {
     "oasr_tp_unique_id": (C.c_int, [_vp]),
     "oasr_tp_init": (C.c_int, [_vp, _i32, _i32, _vp]),
     "oasr_tp_emulate": (C.c_int, [_vp, _i32]),
+    "oasr_tp_ipc_export": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "oasr_tp_ipc_import": (C.c_int, [_vp, _vp]),
     "oasr_feature_length": (_i32, [C.POINTER(OasrConfig), _i64]),
     "oasr_forward_ctc": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_transcribe_host": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

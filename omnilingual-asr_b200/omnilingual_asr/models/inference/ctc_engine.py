@@ -74,6 +74,23 @@ class CtcEngine:
                         "oasr_tp_init")
         self.tp_world = int(tp_emulate) if tp_emulate and tp_emulate > 1 else int(tp_world)
 
+    def tp_enable_peer_memory(self, max_batch: int, max_samples: int, group=None) -> None:
+        """Switch the tensor-parallel group to the fused peer-memory kernel (all-reduce + residual + LayerNorm over
+        NVLink in one launch).  Collective over `group` (torch.distributed); call before the first forward."""
+        import torch.distributed as dist
+        buf = C.create_string_buffer(64)
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_tp_ipc_export(self._handle, int(max_batch), int(max_samples), C.cast(buf, C.c_void_p)),
+                    "oasr_tp_ipc_export")
+        mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(self.device)
+        world = dist.get_world_size(group)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blob = b"".join(bytes(t.cpu().numpy().tobytes()) for t in gathered)
+        hb = C.create_string_buffer(blob, len(blob))
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_tp_ipc_import(self._handle, C.cast(hb, C.c_void_p)), "oasr_tp_ipc_import")
+
     @staticmethod
     def tp_unique_id() -> bytes:
         """128-byte NCCL id for a tensor-parallel group; rank 0 creates it, the caller broadcasts it."""

@@ -1,5 +1,5 @@
 """Tensor-parallel parity over NCCL: every rank runs its slice of the encoder, rank 0 compares with an unsplit engine.
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_check.py [preset]"""
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_check.py [preset] [fused|nccl]"""
 import os
 import sys
 from pathlib import Path
@@ -32,7 +32,12 @@ if rank == 0:
 dist.broadcast(idt, 0)
 eng = CtcEngine(cfg, device=dev, tp_rank=rank, tp_world=world, tp_id=bytes(idt.cpu().numpy().tobytes()))
 eng.load_state_dict(w)
+mode = sys.argv[2] if len(sys.argv) > 2 else "fused"
+if mode == "fused":
+    eng.tp_enable_peer_memory(wave.shape[0], wave.shape[1])
 res = eng.forward(wave.to(dev), ns, normalised=True, return_hidden=True)
+res2 = eng.forward(wave.to(dev), ns, normalised=True, return_hidden=False)   # second call: epochs keep counting
+assert all((a == b).all() for a, b in zip(res.token_ids, res2.token_ids)), "forward is not repeatable"
 torch.cuda.synchronize()
 # every rank holds the same replicated result
 ids = torch.from_numpy(res.frame_ids.astype(np.int64)).to(dev)
@@ -45,7 +50,7 @@ if rank == 0:
     r0 = ref.forward(wave.to(dev), ns, normalised=True, return_hidden=True)
     err = max(float((res.hidden[b, :nf] - r0.hidden[b, :nf]).norm() / r0.hidden[b, :nf].norm()) for b, nf in enumerate(r0.n_frames))
     same = float(np.mean([np.mean(res.frame_ids[b, :nf] == r0.frame_ids[b, :nf]) for b, nf in enumerate(r0.n_frames)]))
-    print(f"tp{world} {name}: hidden rel err vs unsplit {err:.2e}, frame-id agreement {same:.4f}")
+    print(f"tp{world} {name} [{mode}]: hidden rel err vs unsplit {err:.2e}, frame-id agreement {same:.4f}")
     assert err < 5e-3 and same >= 0.97
     print("TP OK")
 dist.barrier()

@@ -10,12 +10,13 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("world", [2])
-def test_tp_over_nccl_matches_single_gpu(world):
+@pytest.mark.parametrize("world,mode", [(2, "nccl"), (2, "fused")])
+def test_tp_matches_single_gpu(world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(ROOT / "scripts" / "tp_check.py")],
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", str(ROOT / "scripts" / "tp_check.py"),
+                        "wide2l", mode],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "TP OK" in r.stdout
