@@ -59,7 +59,9 @@ enum {
 
 /* forward flags */
 enum {
-  OASR_FLAG_INPUT_NORMALISED = 1 /* skip the per-window normalisation (a8) */
+  OASR_FLAG_INPUT_NORMALISED = 1, /* skip the per-window normalisation (a8) */
+  OASR_FLAG_INPUT_I16 = 2         /* the waveform pointer holds PCM16 samples (int16, mono, 16 kHz): the conversion
+                                     x / 32768 is fused into the normalisation kernels (device-side audio front end) */
 };
 
 typedef struct OasrConfig {

@@ -367,7 +367,14 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   prof_mark(e, OASR_PROF_WAVE_NORM, st);
   const float* wv = wave_in;
   long long wv_stride = wave_stride;
-  if (!(flags & OASR_FLAG_INPUT_NORMALISED)) {
+  if (flags & OASR_FLAG_INPUT_I16) {
+    OASR_REQUIRE(!(flags & OASR_FLAG_INPUT_NORMALISED), "forward: PCM16 input cannot be flagged as normalised");
+    OASR_TRY(wave_norm_i16(reinterpret_cast<const short*>(wave_in), e->wave, e->n_samples_dev, B, L, wave_stride, L,
+                           e->wave_partials, st));
+    e->launches += 2;
+    wv = e->wave;
+    wv_stride = L;
+  } else if (!(flags & OASR_FLAG_INPUT_NORMALISED)) {
     OASR_TRY(wave_norm(wave_in, e->wave, e->n_samples_dev, B, L, wave_stride, L, e->wave_partials, st));
     e->launches += 2;
     wv = e->wave;
@@ -979,7 +986,8 @@ int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stri
   const int64_t ws = wave_stride > 0 ? wave_stride : L;
   float* dst = h->wave_raw;
   void* tmp = nullptr;
-  cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)L * 4, wave_host, (size_t)ws * 4, (size_t)L * 4, B,
+  const size_t esz = (flags & OASR_FLAG_INPUT_I16) ? 2 : 4;   // PCM16 windows land as they are: half the H2D bytes
+  cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)L * esz, wave_host, (size_t)ws * esz, (size_t)L * esz, B,
                                      cudaMemcpyHostToDevice, st);
   int rc = OASR_OK;
   if (ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("H2D waveform: ") + cudaGetErrorString(ce));

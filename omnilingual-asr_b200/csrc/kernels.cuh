@@ -11,6 +11,10 @@ constexpr int WAVE_NORM_SLICES = 64;
 int wave_norm(const float* in, float* out, const int* n_samples, int B, int L, long long in_stride,
               long long out_stride, double* partials, cudaStream_t stream);
 
+// same from PCM16 samples (device-side audio front end: int16 -> fp32 / 32768 fused into the normalisation)
+int wave_norm_i16(const short* in, float* out, const int* n_samples, int B, int L, long long in_stride,
+                  long long out_stride, double* partials, cudaStream_t stream);
+
 // a9: Conv1d(1->512, k=10, s=5) + bias + LayerNorm(512) + GELU -> bf16 channels-last.
 // in [B, L] fp32 (row stride in_stride); out [B, out_rows_stride rows, 512] bf16; T0 = (L-10)/5+1 rows written.
 int fe_layer0(const float* wave, long long in_stride, int B, int L, const float* w /*[10][512]*/, const float* bias,

@@ -22,16 +22,21 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // a8 wave normalisation: pass 1 = per-slice (sum, sum of squares) in fp64, pass 2 = normalise.
 // grid (WAVE_NORM_SLICES, B), 256 threads.
 // ---------------------------------------------------------------------------------------------
-__global__ void wave_stats_kernel(const float* __restrict__ in, const int* __restrict__ n_samples, int L,
+// Sample loads: fp32 as is, PCM16 scaled by 1/32768 (exact in fp32: identical to a host-side conversion).
+__device__ __forceinline__ float load_sample(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float load_sample(const short* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
+
+template <typename TIn>
+__global__ void wave_stats_kernel(const TIn* __restrict__ in, const int* __restrict__ n_samples, int L,
                                   long long in_stride, double* __restrict__ partials) {
   const int b = blockIdx.y, slice = blockIdx.x;
   const int n = min(n_samples[b], L);
   const int per = (n + WAVE_NORM_SLICES - 1) / WAVE_NORM_SLICES;
   const int lo = slice * per, hi = min(n, lo + per);
-  const float* x = in + (long long)b * in_stride;
+  const TIn* x = in + (long long)b * in_stride;
   double s = 0.0, ss = 0.0;
   for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const double v = (double)__ldg(x + i);
+    const double v = (double)load_sample(x + i);
     s += v;
     ss += v * v;
   }
@@ -55,7 +60,8 @@ __global__ void wave_stats_kernel(const float* __restrict__ in, const int* __res
   }
 }
 
-__global__ void wave_apply_kernel(const float* __restrict__ in, float* __restrict__ out,
+template <typename TIn>
+__global__ void wave_apply_kernel(const TIn* __restrict__ in, float* __restrict__ out,
                                   const int* __restrict__ n_samples, int L, long long in_stride, long long out_stride,
                                   const double* __restrict__ partials) {
   const int b = blockIdx.y, slice = blockIdx.x;
@@ -77,9 +83,9 @@ __global__ void wave_apply_kernel(const float* __restrict__ in, float* __restric
   const float mean = sh_mean, rstd = sh_rstd;
   const int per = (L + WAVE_NORM_SLICES - 1) / WAVE_NORM_SLICES;
   const int lo = slice * per, hi = min(L, lo + per);
-  const float* x = in + (long long)b * in_stride;
+  const TIn* x = in + (long long)b * in_stride;
   float* y = out + (long long)b * out_stride;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = i < n ? (__ldg(x + i) - mean) * rstd : 0.f;
+  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = i < n ? (load_sample(x + i) - mean) * rstd : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -286,8 +292,18 @@ int wave_norm(const float* in, float* out, const int* n_samples, int B, int L, l
               long long out_stride, double* partials, cudaStream_t stream) {
   OASR_REQUIRE(in && out && n_samples && partials && B > 0 && L > 0, "wave_norm: bad arguments");
   dim3 grid(WAVE_NORM_SLICES, B);
-  wave_stats_kernel<<<grid, 256, 0, stream>>>(in, n_samples, L, in_stride, partials);
-  wave_apply_kernel<<<grid, 256, 0, stream>>>(in, out, n_samples, L, in_stride, out_stride, partials);
+  wave_stats_kernel<float><<<grid, 256, 0, stream>>>(in, n_samples, L, in_stride, partials);
+  wave_apply_kernel<float><<<grid, 256, 0, stream>>>(in, out, n_samples, L, in_stride, out_stride, partials);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+int wave_norm_i16(const short* in, float* out, const int* n_samples, int B, int L, long long in_stride,
+                  long long out_stride, double* partials, cudaStream_t stream) {
+  OASR_REQUIRE(in && out && n_samples && partials && B > 0 && L > 0, "wave_norm: bad arguments");
+  dim3 grid(WAVE_NORM_SLICES, B);
+  wave_stats_kernel<short><<<grid, 256, 0, stream>>>(in, n_samples, L, in_stride, partials);
+  wave_apply_kernel<short><<<grid, 256, 0, stream>>>(in, out, n_samples, L, in_stride, out_stride, partials);
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }

@@ -17,6 +17,7 @@ ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_UNSUPPORTED = -1, -2, -3, -4
 DTYPE_F32, DTYPE_BF16 = 0, 1
 EPI_BF16, EPI_BF16_GELU, EPI_F32, EPI_F32_RESID, EPI_ARGMAX, EPI_LN_GELU_BF16, EPI_F32_GELU_RESID = range(7)
 FLAG_INPUT_NORMALISED = 1
+FLAG_INPUT_I16 = 2
 PROF_CATEGORIES = ("wave_norm", "fe_layer0", "fe_conv_1_6", "layernorm", "feature_proj", "posconv", "qkv_gemm",
                    "attention", "outproj_gemm", "ffn1_gemm", "ffn2_gemm", "ctc_head_argmax", "decode", "tp_allreduce", "end")
 

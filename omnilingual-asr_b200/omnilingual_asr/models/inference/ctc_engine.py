@@ -171,17 +171,29 @@ class CtcEngine:
     def transcribe_host(self, wave: np.ndarray | torch.Tensor, n_samples: Sequence[int], *,
                         normalised: bool = False, return_frame_ids: bool = False) -> CtcBatchResult:
         """Same from host memory through oasr_transcribe_host (H2D + forward + D2H inside the call)."""
+        flags = N.FLAG_INPUT_NORMALISED if normalised else 0
         if isinstance(wave, torch.Tensor):
-            if wave.device.type != "cpu" or wave.dtype != torch.float32 or wave.dim() != 2 or wave.stride(1) != 1:
-                raise ValueError("wave must be a [B, L] float32 CPU tensor with unit inner stride")
+            if wave.device.type != "cpu" or wave.dtype not in (torch.float32, torch.int16) or wave.dim() != 2 \
+                    or wave.stride(1) != 1:
+                raise ValueError("wave must be a [B, L] float32 (or PCM16 int16) CPU tensor with unit inner stride")
             B, L = wave.shape
             stride = wave.stride(0)
+            if wave.dtype == torch.int16:
+                flags |= N.FLAG_INPUT_I16
         else:
-            wave = np.ascontiguousarray(wave, dtype=np.float32)
+            wave = np.asarray(wave)
             if wave.ndim != 2:
                 raise ValueError("wave must be [B, L]")
+            if wave.dtype != np.int16:
+                wave = np.asarray(wave, dtype=np.float32)
+            if wave.strides[1] != wave.itemsize or wave.strides[0] % wave.itemsize:
+                wave = np.ascontiguousarray(wave)
             B, L = wave.shape
-            stride = L
+            stride = wave.strides[0] // wave.itemsize      # rows may be a strided view of one long recording
+            if wave.dtype == np.int16:                      # PCM16: converted on the device (half the H2D bytes)
+                flags |= N.FLAG_INPUT_I16
+        if (flags & N.FLAG_INPUT_I16) and normalised:
+            raise ValueError("PCM16 input cannot be flagged as normalised")
         T = self.feature_length(L)
         ns = (C.c_int32 * B)(*[int(v) for v in n_samples])
         out_ids = np.empty((B, max(T, 1)), dtype=np.int32)
@@ -191,7 +203,7 @@ class CtcEngine:
         with self._lock, torch.cuda.device(self.device):
             N.check(self._lib.oasr_transcribe_host(
                 self._handle, N.ptr(wave), stride, C.cast(ns, C.c_void_p), B, L,
-                N.FLAG_INPUT_NORMALISED if normalised else 0, N.ptr(out_ids), N.ptr(out_frames), N.ptr(out_lens),
+                flags, N.ptr(out_ids), N.ptr(out_frames), N.ptr(out_lens),
                 N.ptr(fids), N.stream_ptr()), "oasr_transcribe_host")
         return CtcBatchResult(
             token_ids=[out_ids[b, :out_lens[b]].copy() for b in range(B)],

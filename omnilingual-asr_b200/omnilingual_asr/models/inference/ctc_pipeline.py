@@ -90,11 +90,43 @@ def _resolve_audio(audio: AudioInput, sample_rate: Optional[int]) -> np.ndarray:
     if hasattr(audio, "detach"):  # torch.Tensor
         audio = audio.detach().cpu().float().numpy()
     x = np.asarray(audio)
+    if x.dtype == np.int16 and x.ndim == 1 and int(sample_rate or SAMPLE_RATE) == SAMPLE_RATE:
+        return x   # mono PCM16 at 16 kHz stays as it is: the device converts it (OASR_FLAG_INPUT_I16)
     if x.dtype == np.int16:
         x = x.astype(np.float32) / 32768.0
     if x.ndim == 2 and x.shape[0] < x.shape[1] and x.shape[0] <= 8:
         x = x.T  # [channels, n] -> [n, channels]
     return to_mono_16k(x, int(sample_rate or SAMPLE_RATE))
+
+
+class _pinned:
+    """Page-locks a large host array for the duration of a call (cudaHostRegister); a no-op for small arrays, fake
+    engines or when registration is refused."""
+
+    MIN_BYTES = 64 << 20
+
+    def __init__(self, arr: np.ndarray, engine: Any) -> None:
+        self.ptr = None
+        if getattr(engine, "device", None) is None or arr.nbytes < self.MIN_BYTES or not arr.flags.c_contiguous:
+            return
+        try:
+            import torch
+            self.rt = torch.cuda.cudart()
+            if int(self.rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
+                self.ptr = arr.ctypes.data
+        except Exception:
+            self.ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        if self.ptr is not None:
+            try:
+                self.rt.cudaHostUnregister(self.ptr)
+            except Exception:
+                pass
+        return False
 
 
 def build_segments(win: WindowTokens, vocab: CtcVocabulary, *, word_timestamps: bool,
@@ -202,10 +234,15 @@ class CTCASRPipeline:
         for b0 in range(lo, hi, self.batch_windows):
             idx = list(range(b0, min(hi, b0 + self.batch_windows)))
             L = max(windows[i][1] for i in idx)
-            batch = np.zeros((len(idx), L), dtype=np.float32)
-            for r, i in enumerate(idx):
-                s, n = windows[i]
-                batch[r, :n] = wave[s:s + n]
+            s0 = windows[idx[0]][0]
+            if all(windows[i] == (s0 + r * L, L) for r, i in enumerate(idx)) and wave.flags.c_contiguous:
+                # full, back-to-back windows: the batch is a [B, L] view of the recording itself (no host copy)
+                batch = wave[s0:s0 + len(idx) * L].reshape(len(idx), L)
+            else:
+                batch = np.zeros((len(idx), L), dtype=wave.dtype if wave.dtype == np.int16 else np.float32)
+                for r, i in enumerate(idx):
+                    s, n = windows[i]
+                    batch[r, :n] = wave[s:s + n]
             ns = [windows[i][1] for i in idx]
             with self._lock:
                 res = self.engine.transcribe_host(batch, ns)
@@ -228,7 +265,8 @@ class CTCASRPipeline:
         _report("transcribing", 1)
         rank, world = self._rank_world()
         lo, hi = shard_range(len(windows), rank, world)
-        mine = self._run_windows(wave, windows, lo, hi)
+        with _pinned(wave, self.engine):      # long recordings: page-lock once so that every window copy is a DMA
+            mine = self._run_windows(wave, windows, lo, hi)
         if world > 1:
             import torch.distributed as dist
             gathered: List[Optional[List[WindowTokens]]] = [None] * world

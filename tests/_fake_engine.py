@@ -20,8 +20,10 @@ class OracleEngine:
         self.calls = []
 
     def transcribe_host(self, wave, n_samples, *, normalised=False, return_frame_ids=False):
-        wave = torch.as_tensor(np.asarray(wave), dtype=torch.float32)
-        self.calls.append((tuple(wave.shape), list(n_samples)))
+        arr = np.asarray(wave)
+        self.calls.append((tuple(arr.shape), list(n_samples)))
+        self.last_dtype = arr.dtype
+        wave = torch.as_tensor(arr.astype(np.float32) / 32768.0 if arr.dtype == np.int16 else arr, dtype=torch.float32)
         if not normalised:
             wave = O.wave_layer_norm(wave, n_samples)
         out = O.forward(self.w, wave, n_samples, self.ocfg)

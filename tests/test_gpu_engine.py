@@ -242,3 +242,20 @@ def test_tensor_parallel_rejects_bad_splits(device):
         CtcEngine(product_cfg(ocfg), device=device, tp_emulate=2)
     with pytest.raises(ValueError):
         CtcEngine(product_cfg(O.PRESETS["tiny"]), device=device, tp_emulate=3)
+
+
+def test_pcm16_front_end_equals_host_conversion(device):
+    """OASR_FLAG_INPUT_I16: int16 windows converted inside the normalisation kernels give the ids of the same
+    samples converted on the host (x / 32768 is exact in fp32); rows may be a strided view of one recording."""
+    ocfg, w, eng = make_engine("tiny", device)
+    rng = np.random.default_rng(3)
+    L = 16000
+    rec = (rng.standard_normal(3 * L + 500) * 4000).astype(np.int16)
+    view = rec[: 3 * L].reshape(3, L)
+    ns = [L, L, L - 777]
+    a = eng.transcribe_host(view, ns, return_frame_ids=True)
+    f = view.astype(np.float32) / 32768.0
+    b = eng.transcribe_host(f, ns, return_frame_ids=True)
+    assert (a.frame_ids == b.frame_ids).all()
+    assert all((x == y).all() for x, y in zip(a.token_ids, b.token_ids))
+    eng.close()

@@ -203,3 +203,19 @@ def test_split_on_silence_shapes_segments():
     assert len(one) == 1 and len(two) == 2 and two[0].text == "ab" and two[1].text == "cd"
     assert P.build_segments(P.WindowTokens(0, 0, 100, 0, np.array([], np.int32), np.array([], np.int32)), v,
                             word_timestamps=True, split_gap_sec=None, language=None) == []
+
+
+def test_pcm16_recording_stays_int16_and_full_windows_are_views(engine):
+    """Mono PCM16 at 16 kHz is handed to the engine as it is (the device converts it: OASR_FLAG_INPUT_I16), full
+    back-to-back windows as [B, L] views of the recording; the result equals the float32 route."""
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
+    rng = np.random.default_rng(7)
+    win = 8000
+    pcm = (rng.standard_normal(3 * win + 1234) * 3000).astype(np.int16)
+    pipe = CTCASRPipeline(engine.cfg, engine=engine, window_seconds=win / 16000, batch_windows=2, distributed=False)
+    a = pipe.transcribe_chunked(pcm, sample_rate=16000)
+    assert engine.last_dtype == np.int16
+    assert [c[0] for c in engine.calls[-2:]] == [(2, win), (2, win)]      # [w0, w1] as a view, [w2, ragged tail] copied
+    b = pipe.transcribe_chunked(pcm.astype(np.float32) / 32768.0, sample_rate=16000)
+    assert engine.last_dtype == np.float32
+    assert [(s.start, s.end, s.text) for s in a.segments] == [(s.start, s.end, s.text) for s in b.segments]
