@@ -302,11 +302,24 @@ def run_ours(args):
     g_flops = sum(fl[n] for n in gemm_names) * B * args.steps
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    # 1B shapes only): mean over the four encoder GEMMs, like flops_per_launch
+    traffic, ncu_note = None, None
+    try:
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if args.model == "omniASR_CTC_1B" and B == 32:
+            per = [tj["kernels"][n]["traffic_bytes"] for n in gemm_names]
+            traffic = sum(per) / len(per)
+            ncu_note = {n: {"traffic_bytes": tj["kernels"][n]["traffic_bytes"],
+                            "tensor_pipe_active_pct": tj["kernels"][n]["tensor_pipe_active_pct"]} for n in gemm_names}
+    except Exception:
+        pass
     roofline = {
         "kernel": "gemm_kernel<256,*> (tcgen05 GEMM: encoder QKV / out-proj / FFN1 / FFN2)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
-        "traffic": None,
+        "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu)",
+        "ncu": ncu_note,
         "flops_per_launch": g_flops / max(g_cnt, 1), "avg_launch_ms": g_ms / max(g_cnt, 1),
         "share_of_step": g_ms / total_stage_ms,
         "whole_path_tflops": sum(fl.values()) * B * (1 if tp > 1 else world) * args.steps / (dev_ms / 1e3) / 1e12,

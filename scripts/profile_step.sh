@@ -15,7 +15,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-fi
 echo "launch list rc=$?"
 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:'gemm_kernel|attention_v3|layernorm|fe_layer0' -s 348 -c 17 -f -o $OUT/${TAG}_full $CMD \
+    -k regex:'gemm_kernel|attention_v|layernorm|fe_layer0' -s 348 -c 17 -f -o $OUT/${TAG}_full $CMD \
     > $OUT/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la $OUT
