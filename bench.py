@@ -33,6 +33,7 @@ import torch  # noqa: E402
 
 WINDOW_SEC = 30.0
 SR = 16000
+_JSON_OUT = sys.stdout
 METRIC = "audio-sec/sec (inverse RTF)"
 UNIT = "audio-s/s"
 
@@ -187,7 +188,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def run_ours(args):
@@ -349,13 +350,20 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_windows} x 30 s windows, one pass, PyTorch eager fp32 oracle "
                                           f"({times[0]:.1f} s)"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 from native code (NCCL prints its version
+    # banner there) are pointed at stderr, the JSON line goes to the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    global _JSON_OUT
+    _JSON_OUT = os.fdopen(saved, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
