@@ -540,12 +540,13 @@ int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T
                    cudaStream_t stream) {
   static const int version = [] {
     const char* e = std::getenv("OASR_ATTN");
-    return e != nullptr ? std::atoi(e) : 4;
+    return e != nullptr ? std::atoi(e) : 6;
   }();
   if (version == 1) return attention_bf16_v1(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version == 2) return attention_bf16_v2(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version == 3) return attention_bf16_v3(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version == 5) return attention_bf16_v5(qkv, out, n_frames, B, T, H, hd, scale, stream);   // experiment, see v5
+  if (version == 6 && hd <= 80) return attention_bf16_v6(qkv, out, n_frames, B, T, H, hd, scale, stream);
   return attention_bf16_v4(qkv, out, n_frames, B, T, H, hd, scale, stream);
 }
 

@@ -1,0 +1,621 @@
+// Bidirectional self-attention on tcgen05, sixth version (a14), head_dim <= 80 (300M, 1B): v4's pipeline with THREE
+// query tiles (384 queries) per CTA and 48-key blocks.  v4 keeps two softmax warps per SM sub-partition; each spends
+// ~450 cycles per key block outside its exponentials (TMEM loads and stores, fences, mbarrier round trips) and the
+// MUFU pipe idles whenever both are there (63 % busy in steady state, profiles/r1_notes.md).  A third tile gives every
+// sub-partition a third, independent softmax warp; the shorter key block (3 S + 3 P + 3 O = 480 TMEM columns at
+// head_dim 80) hands S back at the very start of a block, and the three tiles are started a third of a period apart
+// (tile X+1's first S is issued when tile X has read its first S).  K/V tiles are fetched once per 384 queries.
+// Same numerics contract, masks, reference handling and epilogue as v4.
+//
+// TMEM columns: S_A S_B S_C (48 each) | P_A P_B P_C (24 used of 32 each) | O_A O_B O_C (head_dim each).
+// Warps: 0-3 / 4-7 / 8-11 softmax + epilogue of tiles A / B / C (warp w owns TMEM lanes [32(w%4), +32)),
+// 12 TMA producer, 13 MMA issuer / TMEM allocator.
+#include "host_util.h"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+namespace oasr {
+namespace {
+
+constexpr int NT = 3;                       // query tiles per CTA
+constexpr int ATT_THREADS = (NT * 4 + 2) * 32;
+constexpr int BQ = 128;
+constexpr int MAX_KV_STAGES = 8;
+constexpr int TMEM_COLS = 512;
+constexpr float REF_MARGIN = 80.f;   // a chunk maximum more than 2^80 above the reference moves the reference
+
+__host__ __device__ constexpr int att_bkv(int) { return 48; }
+__host__ __device__ constexpr int round16(int v) { return (v + 15) & ~15; }
+
+// Column chunks of a [rows][HD] bf16 K-major tile: greedy 64 / 32 / 16 (128B / 64B / 32B swizzle); see v3.
+__host__ __device__ constexpr int qk_nchunks(int hd) {
+  int n = 0;
+  for (int w = 64; w >= 16; w >>= 1)
+    while (hd >= w) {
+      hd -= w;
+      ++n;
+    }
+  return n;
+}
+__host__ __device__ constexpr int qk_w(int hd, int i) {
+  int n = 0;
+  for (int w = 64; w >= 16; w >>= 1)
+    while (hd >= w) {
+      if (n == i) return w;
+      hd -= w;
+      ++n;
+    }
+  return 0;
+}
+__host__ __device__ constexpr int qk_col(int hd, int i) {
+  int c = 0;
+  for (int j = 0; j < i; ++j) c += qk_w(hd, j);
+  return c;
+}
+__host__ __device__ constexpr int v_w(int hd) { return hd % 64 == 0 ? 64 : (hd % 32 == 0 ? 32 : 16); }
+__host__ __device__ constexpr uint32_t swz_of(int w) { return w == 64 ? SWZ_128B : (w == 32 ? SWZ_64B : SWZ_32B); }
+__host__ __device__ constexpr uint32_t desc_hi(int sbo_bytes, uint32_t layout) {
+  return uint32_t((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
+
+struct Attn6Params {
+  int kv_stages;
+  int T, H, d;
+  float scale_log2e;
+  const int* n_frames;
+  __nv_bfloat16* out;
+  long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
+};
+constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
+#define ATT_TRACE(role, ev)                                                                                 \
+  do {                                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (ev) < TRACE_EVENTS) \
+      p.trace[(role) * TRACE_EVENTS + (ev)] = clock64();                                                    \
+  } while (0)
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t bf16x2_scale(uint32_t v, uint32_t f2) {
+  uint32_t r;
+  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(f2));
+  return r;
+}
+
+// 2^x for a packed pair on the FMA pipe (no MUFU): Cody-Waite split with the round-to-nearest magic constant,
+// degree-4 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.7e-6, a 1/1400 of a bf16 ulp), exponent inserted
+// with one integer multiply-add per element.  x must be in [-126, 127].
+__device__ __forceinline__ float2 exp2_fma2(float2 x) {
+  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));          // low mantissa bits = round(x)
+  const float2 xi = fadd2(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(xi, make_float2(-1.f, -1.f), x);
+  float2 q = ffma2(make_float2(9.570069611e-03f, 9.570069611e-03f), f, make_float2(5.591785908e-02f, 5.591785908e-02f));
+  q = ffma2(q, f, make_float2(2.402474582e-01f, 2.402474582e-01f));
+  q = ffma2(q, f, make_float2(6.931217909e-01f, 6.931217909e-01f));
+  q = ffma2(q, f, make_float2(9.999992847e-01f, 9.999992847e-01f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+
+// Everything a reference move has to touch.
+template <int HD>
+struct RowState {
+  float m_ref;       // integer-valued reference in the log2 domain
+  float sum;         // running sum of the unrounded P of finished blocks
+  float2 sm[2];      // pair-accumulators of the block in flight
+  uint32_t t_o;      // TMEM address of this row's O
+  uint64_t* o_done;  // P.V_X(j) has retired
+  int j;             // key block in flight
+};
+
+// Moves the reference of the rows whose `need` = chunk maximum (log2 domain) - m_ref exceeds REF_MARGIN.  NPK =
+// packed P words of the block computed so far.  Warp-collective (TMEM accesses): called under a warp-uniform branch.
+template <int HD, int NPK, int PKN>
+__device__ __forceinline__ void move_reference(float need, RowState<HD>& rs, uint32_t (&pk)[PKN]) {
+  const float k = need > REF_MARGIN ? ceilf(need) : 0.f;
+  const float f = ex2(-k);   // exact (k is an integer); 0 when the old reference was hopelessly low
+  rs.m_ref += k;
+  rs.sum *= f;
+  rs.sm[0].x *= f; rs.sm[0].y *= f; rs.sm[1].x *= f; rs.sm[1].y *= f;
+  const uint32_t f2 = pack_bf16x2(f, f);
+#pragma unroll
+  for (int i = 0; i < NPK; ++i) pk[i] = bf16x2_scale(pk[i], f2);
+  if (rs.j > 0) {
+    mbar_wait(rs.o_done, (rs.j - 1) & 1);   // P.V(j-1) has finished updating O; P.V(j) cannot start before our p_full
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16(rs.t_o + cc, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+      tmem_st16(rs.t_o + cc, v);
+    }
+    tmem_st_wait();
+  }
+}
+
+// W scores of a row (columns [BASE, BASE+W) of the block): reference check, P = 2^(s c - m_ref) -> pk, sums.
+// POLY > 0: every POLY-th pair takes the FMA-pipe exponential instead of MUFU.EX2 (the MUFU pipe is the floor of the
+// kernel: two softmax warps per SM sub-partition cannot issue more than ~1 MUFU per 10 cycles between them).
+template <int HD, int BASE, int W, bool MASKED, int POLY, int PKN>
+__device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, float c, RowState<HD>& rs,
+                                              uint32_t (&pk)[PKN]) {
+  float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+#pragma unroll
+  for (int i = 0; i < W; ++i)
+    if (!MASKED || BASE + i < ncols) cm4[(i >> 1) & 3] = fmaxf(cm4[(i >> 1) & 3], __uint_as_float(v[i]));
+  const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
+  if (BASE == 0 && rs.j == 0) {
+    rs.m_ref = ceilf(cm * c);   // first chunk of the row (column 0 is always a valid key)
+  } else {
+    const float need = fmaf(cm, c, -rs.m_ref);
+    if (__any_sync(0xffffffffu, need > REF_MARGIN)) move_reference<HD, BASE / 2>(need, rs, pk);
+  }
+  const float2 c2 = make_float2(c, c), nm2 = make_float2(-rs.m_ref, -rs.m_ref);
+#pragma unroll
+  for (int i = 0; i < W; i += 2) {
+    const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
+    float p0, p1;
+    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+      const float2 e = exp2_fma2(make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f)));
+      p0 = e.x;
+      p1 = e.y;
+    } else {
+      p0 = ex2(x.x);
+      p1 = ex2(x.y);
+    }
+    if (MASKED) {
+      if (BASE + i >= ncols) p0 = 0.f;
+      if (BASE + i + 1 >= ncols) p1 = 0.f;
+    }
+    rs.sm[(i >> 1) & 1] = fadd2(rs.sm[(i >> 1) & 1], make_float2(p0, p1));
+    pk[(BASE + i) >> 1] = pack_bf16x2(p0, p1);
+  }
+}
+
+template <int HD, int POLY>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
+                    const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
+                    const __grid_constant__ CUtensorMap tmk32, const __grid_constant__ CUtensorMap tmk16,
+                    const Attn6Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BKV = att_bkv(HD);
+  constexpr int PSLOT = round16(BKV / 2);
+  constexpr int TM_S = 0, TM_P = NT * BKV, TM_O = NT * BKV + NT * PSLOT;
+  static_assert(TM_O + NT * HD <= TMEM_COLS, "TMEM budget");
+  constexpr int NQK = qk_nchunks(HD);
+  constexpr int VW = v_w(HD);
+  constexpr int NV = HD / VW;
+  constexpr int q_tile_bytes = BQ * HD * 2;
+  constexpr int kv_tile_bytes = BKV * HD * 2;
+  const int KS = p.kv_stages;
+  uint8_t* sQ = smem;                     // [NT tiles]
+  uint8_t* sKV = sQ + NT * q_tile_bytes;  // [stage][K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + KS * 2 * kv_tile_bytes);
+  uint64_t* q_full = bars;                       // 1
+  uint64_t* kv_full = bars + 1;                  // MAX_KV_STAGES
+  uint64_t* kv_empty = kv_full + MAX_KV_STAGES;  // MAX_KV_STAGES
+  uint64_t* s_full = kv_empty + MAX_KV_STAGES;   // NT (per query tile): S_X(j) is in TMEM
+  uint64_t* s_free = s_full + NT;                // NT: S_X(j) has been read into registers
+  uint64_t* p_full = s_free + NT;                // NT: P_X(j) is in TMEM
+  uint64_t* o_done = p_full + NT;                // NT: P.V_X(j) has retired (O updated, P buffer free)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NT * BQ);
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_keys = min(p.n_frames ? p.n_frames[b] : p.T, p.T);
+  const int nblk = (n_keys + BKV - 1) / BKV;
+
+  if (nblk == 0) {  // fully padded window: attention output is defined as zero
+    for (int i = threadIdx.x; i < NT * BQ * (HD / 8); i += blockDim.x) {
+      const int r = i / (HD / 8), c8 = i % (HD / 8);
+      if (q0 + r < p.T)
+        reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * p.d + h * HD)[c8] = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+
+  if (warp == NT * 4 && lane == 0) {
+    tma_prefetch_desc(&tmq64);
+    tma_prefetch_desc(&tmk64);
+    tma_prefetch_desc(&tmq16);
+    tma_prefetch_desc(&tmk16);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < MAX_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < NT; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == NT * 4 + 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == NT * 4) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      const int qcol = h * HD, kcol = p.d + h * HD, vcol = 2 * p.d + h * HD;
+      auto qmap = [&](int w) { return w == 64 ? &tmq64 : (w == 32 ? &tmq32 : &tmq16); };
+      auto kmap = [&](int w) { return w == 64 ? &tmk64 : (w == 32 ? &tmk32 : &tmk16); };
+      mbar_arrive_expect_tx(q_full, NT * q_tile_bytes);
+#pragma unroll
+      for (int X = 0; X < NT; ++X)
+#pragma unroll
+        for (int c = 0; c < NQK; ++c)
+          tma_load_3d(sQ + X * q_tile_bytes + 2 * BQ * qk_col(HD, c), qmap(qk_w(HD, c)), q_full, qcol + qk_col(HD, c),
+                      q0 + X * BQ, b);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        uint8_t* sK = sKV + s * 2 * kv_tile_bytes;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * kv_tile_bytes);
+#pragma unroll
+        for (int c = 0; c < NQK; ++c)    // K: same chunking as Q
+          tma_load_3d(sK + 2 * BKV * qk_col(HD, c), kmap(qk_w(HD, c)), &kv_full[s], kcol + qk_col(HD, c), j * BKV, b);
+#pragma unroll
+        for (int c = 0; c < NV; ++c)     // V: NV uniform chunks of VW columns
+          tma_load_3d(sK + kv_tile_bytes + c * (2 * BKV * VW), kmap(VW), &kv_full[s], vcol + c * VW, j * BKV, b);
+        if (++s == KS) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == NT * 4 + 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    // Warp-uniform control flow; one elected lane issues.  Static order per key block j:
+    //   p_full_B(j-1) -> P.V_B(j-1), release K/V(j-1);  s_free_A(j) -> S_A(j+1);  s_free_B(j) -> S_B(j+1);
+    //   p_full_A(j) -> P.V_A(j)
+    // (the K/V release precedes the wait for block j+1 so that two stages are enough).
+    const bool issuer = elect_one();
+    constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
+    constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
+    mbar_wait(q_full, 0);
+    const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
+    const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
+    auto issue_s = [&](int X, int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
+      const uint32_t q_lo = sq_lo + X * (q_tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
+      const uint32_t k_lo = skv_lo + st * (2 * kv_tile_bytes >> 4) + (1u << 16);
+      const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
+      bool first = true;
+#pragma unroll
+      for (int c = 0; c < NQK; ++c) {
+        const int w = qk_w(HD, c);
+        const uint32_t hi = desc_hi(16 * w, swz_of(w));   // K-major: rows of 2w bytes, 8-row groups of 16w bytes
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < w / 16) {
+            const uint32_t qoff = (2 * BQ * qk_col(HD, c) + kk * 32) >> 4;
+            const uint32_t koff = (2 * BKV * qk_col(HD, c) + kk * 32) >> 4;
+            if (issuer) umma_ss(d_tmem, desc64(hi, q_lo + qoff), desc64(hi, k_lo + koff), idesc_s, first ? 0u : 1u);
+            first = false;
+          }
+        }
+      }
+      if (issuer) umma_commit(&s_full[X]);
+    };
+    // O_X += P_X V for the V tile in stage st.  V is MN-major: kv rows of 2*VW bytes, 8-row groups SBO = 16*VW
+    // apart, the NV column chunks LBO = 2*BKV*VW apart.
+    auto issue_pv = [&](int X, int st, int j) {
+      constexpr uint32_t hi = desc_hi(16 * VW, swz_of(VW));
+      const uint32_t v_lo = skv_lo + ((st * 2 * kv_tile_bytes + kv_tile_bytes) >> 4) + (uint32_t((2 * BKV * VW) >> 4) << 16);
+      const uint32_t d_tmem = tmem_base + TM_O + X * HD;
+      const uint32_t p_tmem = tmem_base + TM_P + X * PSLOT;
+#pragma unroll
+      for (int kk = 0; kk < BKV / 16; ++kk)
+        if (issuer)
+          umma_ts(d_tmem, p_tmem + kk * 8, desc64(hi, v_lo + ((kk * 32 * VW) >> 4)), idesc_o, (j | kk) != 0 ? 1u : 0u);
+      if (issuer) umma_commit(&o_done[X]);
+    };
+    // Static order per key block j, the order of the events when the tiles run a third of a period apart:
+    //   s_free_A(j) -> S_A(j+1);  p_full_C(j-1) -> P.V_C(j-1), release K/V(j-1);  s_free_B(j) -> S_B(j+1);
+    //   p_full_A(j) -> P.V_A(j);  s_free_C(j) -> S_C(j+1);  p_full_B(j) -> P.V_B(j)
+    // In block 0 tile X+1's first S is issued when tile X has read its own: that sets the offsets.  Needs >= 3 K/V
+    // stages (block j+1 is awaited before block j-1 is released).  A polling scheduler (mbarrier.test_wait on all
+    // hand-off barriers, issue whatever is ready) was tried and lost: every test is a ~150-cycle round trip and the
+    // busy warp takes issue slots from the three softmax warps of its sub-partition (profiles/r1_notes.md).
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_s(0, 0);
+    int st_prev = 0, st = 0, st_next = 1;
+    uint32_t ph_next = 0u;   // kv_full parity of block j+1
+    for (int j = 0; j < nblk; ++j) {
+      const bool more = j + 1 < nblk;
+      if (more) mbar_wait(&kv_full[st_next], ph_next);
+      mbar_wait(&s_free[0], j & 1);
+      tc_fence_after();
+      if (j == 0) issue_s(1, 0);
+      if (more) issue_s(0, st_next);
+      if (j > 0) {
+        mbar_wait(&p_full[2], (j - 1) & 1);
+        tc_fence_after();
+        issue_pv(2, st_prev, j - 1);
+        if (issuer) umma_commit(&kv_empty[st_prev]);   // K/V of block j-1: every MMA reading them has been issued
+        __syncwarp();
+      }
+      mbar_wait(&s_free[1], j & 1);
+      tc_fence_after();
+      if (j == 0) issue_s(2, 0);
+      if (more) issue_s(1, st_next);
+      if (lane == 0) ATT_TRACE(0, j * 2);
+      mbar_wait(&p_full[0], j & 1);
+      tc_fence_after();
+      issue_pv(0, st, j);
+      if (lane == 0) ATT_TRACE(0, j * 2 + 1);
+      if (more) {
+        mbar_wait(&s_free[2], j & 1);
+        tc_fence_after();
+        issue_s(2, st_next);
+      }
+      mbar_wait(&p_full[1], j & 1);
+      tc_fence_after();
+      issue_pv(1, st, j);
+      st_prev = st;
+      st = st_next;
+      if (++st_next == KS) {
+        st_next = 0;
+        ph_next ^= 1;
+      }
+    }
+    mbar_wait(&p_full[2], (nblk - 1) & 1);
+    tc_fence_after();
+    issue_pv(2, st_prev, nblk - 1);
+  } else {
+    // ---------------------------------------------------------------- softmax + epilogue (warps 0-11)
+    const int X = warp >> 2;                     // query tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;        // row within the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_lane + TM_S + X * BKV;
+    const uint32_t t_p = t_lane + TM_P + X * PSLOT;
+    const float c = p.scale_log2e;
+    RowState<HD> rs;
+    rs.m_ref = 0.f;
+    rs.sum = 0.f;
+    rs.t_o = t_lane + TM_O + X * HD;
+    rs.o_done = &o_done[X];
+    auto signal_s_free = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[X]);
+    };
+    uint32_t va[32], vb[16];
+    mbar_wait(&s_full[X], 0);
+    tc_fence_after();
+    tmem_ld32(t_s, va);
+    tmem_ld16(t_s + 32, vb);
+    for (int j = 0; j < nblk; ++j) {
+      const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
+      rs.j = j;
+      rs.sm[0] = make_float2(0.f, 0.f);
+      rs.sm[1] = make_float2(0.f, 0.f);
+      uint32_t pk[BKV / 2];
+      const bool tr = (warp & 3) == 0 && lane == 0;
+      if (tr) ATT_TRACE(1 + X, j * 6);
+      // va / vb: columns [0,32) / [32,48) of S(j), requested at the end of the previous iteration: S goes back to
+      // the MMA warp before the first exponential
+      tmem_ld_wait_on(va);
+      tmem_ld_wait_on16(vb);
+      signal_s_free();
+      if (tr) ATT_TRACE(1 + X, j * 6 + 1);
+      static_assert(BKV == 48, "key block");
+      if (ncols == BKV) {
+        softmax_chunk<HD, 0, 32, false, POLY>(va, ncols, c, rs, pk);
+        if (tr) ATT_TRACE(1 + X, j * 6 + 2);
+        softmax_chunk<HD, 32, 16, false, POLY>(vb, ncols, c, rs, pk);
+      } else {
+        softmax_chunk<HD, 0, 32, true, POLY>(va, ncols, c, rs, pk);
+        if (tr) ATT_TRACE(1 + X, j * 6 + 2);
+        softmax_chunk<HD, 32, 16, true, POLY>(vb, ncols, c, rs, pk);
+      }
+      if (tr) ATT_TRACE(1 + X, j * 6 + 4);
+      // S(j+1) was issued when s_free(j) arrived, i.e. long ago: request its first two chunks now so that the TMEM
+      // read latency hides under the P hand-off below
+      if (j + 1 < nblk) {
+        mbar_wait(&s_full[X], (j + 1) & 1);
+        tc_fence_after();
+        tmem_ld32(t_s, va);
+        tmem_ld16(t_s + 32, vb);
+      }
+      {
+        const float2 t = fadd2(rs.sm[0], rs.sm[1]);
+        rs.sum += t.x + t.y;
+      }
+      // The P buffer is free once P.V_X(j-1) has retired.  S_X(j+1) was issued after P.V_X(j-1) by the same thread and
+      // tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it; only the last
+      // block has to ask o_done (an mbarrier round trip costs ~150 cycles on this critical path).
+      if (j > 0 && j + 1 >= nblk) {
+        mbar_wait(&o_done[X], (j - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < (BKV / 2) / 16; ++q4) {
+        uint32_t w16[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w16[i] = pk[q4 * 16 + i];
+        tmem_st16(t_p + q4 * 16, w16);
+      }
+      if constexpr ((BKV / 2) % 16 == 8) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w8[i] = pk[(BKV / 2) - 8 + i];
+        tmem_st8(t_p + (BKV / 2) - 8, w8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[X]);
+      if (tr) ATT_TRACE(1 + X, j * 6 + 5);
+    }
+    // epilogue: O / rowsum -> bf16
+    mbar_wait(&o_done[X], (nblk - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / rs.sum;
+    const int qrow = q0 + X * BQ + r;
+    const bool row_ok = qrow < p.T;
+    __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * HD;
+#pragma unroll 1
+    for (int cc = 0; cc < HD; cc += 16) {
+      uint32_t v[16];
+      tmem_ld16(rs.t_o + cc, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint32_t o[8];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2)
+          o[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+        uint4* dst = reinterpret_cast<uint4*>(orow + cc);
+        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == NT * 4 + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+struct AttKey {
+  const void* base;
+  int B, T, d3, bkv;
+  bool operator<(const AttKey& o) const {
+    if (base != o.base) return base < o.base;
+    if (B != o.B) return B < o.B;
+    if (T != o.T) return T < o.T;
+    if (d3 != o.d3) return d3 < o.d3;
+    return bkv < o.bkv;
+  }
+};
+struct AttMaps {
+  CUtensorMap tm[6];
+};
+std::map<AttKey, AttMaps> g_att6_tmaps;
+std::mutex g_att6_mu;
+
+}  // namespace
+
+int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+                      cudaStream_t stream) {
+  OASR_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "attention: bad arguments");
+  OASR_REQUIRE(hd % 16 == 0 && hd >= 16 && hd <= 80, "attention v6: head_dim must be a multiple of 16 in [16, 80]");
+  OASR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "attention: buffers must be 16-byte aligned");
+  const int d = H * hd;
+  const int bkv = att_bkv(hd);
+  AttMaps m;
+  {
+    std::lock_guard<std::mutex> g(g_att6_mu);
+    AttKey key{qkv, B, T, 3 * d, bkv};
+    auto it = g_att6_tmaps.find(key);
+    if (it == g_att6_tmaps.end()) {
+      uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
+      uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
+      const uint32_t widths[3] = {64, 32, 16};
+      const CUtensorMapSwizzle swz[3] = {CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_32B};
+      for (int i = 0; i < 3; ++i) {
+        uint32_t qbox[3] = {widths[i], (uint32_t)BQ, 1};
+        uint32_t kbox[3] = {widths[i], (uint32_t)bkv, 1};
+        OASR_TRY(make_tmap_bf16(&m.tm[i], qkv, 3, dims, strides, qbox, swz[i]));
+        OASR_TRY(make_tmap_bf16(&m.tm[3 + i], qkv, 3, dims, strides, kbox, swz[i]));
+      }
+      if (g_att6_tmaps.size() > 1024) g_att6_tmaps.clear();
+      g_att6_tmaps[key] = m;
+    } else {
+      m = it->second;
+    }
+  }
+  Attn6Params p;
+  const int q_tile_bytes = BQ * hd * 2, kv_tile_bytes = bkv * hd * 2;
+  int kv_stages = (227 * 1024 - 2048 - NT * q_tile_bytes) / (2 * kv_tile_bytes);
+  kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
+  OASR_REQUIRE(kv_stages >= 3, "attention: tile does not fit shared memory");
+  p.kv_stages = kv_stages;
+  const int smem_bytes = NT * q_tile_bytes + 2 * kv_tile_bytes * kv_stages + 256 + 1024;
+  p.T = T;
+  p.H = H;
+  p.d = d;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.n_frames = n_frames;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.trace = nullptr;
+  const char* trace_path = std::getenv("OASR_ATT_TRACE");
+  if (trace_path != nullptr) {
+    OASR_CUDA_CHECK(cudaMalloc(&p.trace, 4 * TRACE_EVENTS * sizeof(long long)));
+    OASR_CUDA_CHECK(cudaMemset(p.trace, 0, 4 * TRACE_EVENTS * sizeof(long long)));
+  }
+  dim3 grid((T + NT * BQ - 1) / (NT * BQ), H, B);
+  cudaError_t attr_err = cudaSuccess;
+  // POLY (share of exponentials moved to the FMA pipe): measured 587 / 613 / 580 / 568 us for POLY = 0 / 2 / 3 / 4 at the
+  // 1B shape - within run-to-run noise, the softmax warps are issue/latency-bound, not MUFU-bound - so only the plain
+  // MUFU variant is instantiated.
+#define OASR_ATT_CASE(HDV)                                                                                      \
+  case HDV: {                                                                                                   \
+    static bool attr_done = false;                                                                              \
+    if (!attr_done) {                                                                                           \
+      attr_err = cudaFuncSetAttribute(attention_v6_kernel<HDV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      227 * 1024);                                                              \
+      attr_done = attr_err == cudaSuccess;                                                                      \
+    }                                                                                                           \
+    if (attr_err == cudaSuccess)                                                                                \
+      attention_v6_kernel<HDV, 0><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
+                                                                             m.tm[4], m.tm[5], p);              \
+    break;                                                                                                      \
+  }
+  switch (hd) {
+    OASR_ATT_CASE(16)
+    OASR_ATT_CASE(32)
+    OASR_ATT_CASE(48)
+    OASR_ATT_CASE(64)
+    OASR_ATT_CASE(80)
+    default: return fail(OASR_ERR_UNSUPPORTED, "attention v6: head_dim must be a multiple of 16 in [16, 80]");
+  }
+#undef OASR_ATT_CASE
+  OASR_CUDA_CHECK(attr_err);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  if (p.trace != nullptr) {
+    static long long host[4 * TRACE_EVENTS];
+    OASR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    OASR_CUDA_CHECK(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int r = 0; r < 4; ++r) {
+        for (int e = 0; e < TRACE_EVENTS; ++e) fprintf(f, "%lld ", host[r * TRACE_EVENTS + e]);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
+  return OASR_OK;
+}
+
+}  // namespace oasr
