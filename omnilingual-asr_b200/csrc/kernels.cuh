@@ -47,17 +47,9 @@ int ctc_collapse(const int* frame_ids, const int* n_frames, int B, int T, int bl
 // qkv bf16 [B*T, 3*d] (q | k | v column blocks, head h at columns h*hd), out bf16 [B*T, d].
 int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                    cudaStream_t stream);
-int attention_bf16_v1(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
-                      cudaStream_t stream);
-int attention_bf16_v2(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
-                      cudaStream_t stream);
-int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
-                      cudaStream_t stream);
-int attention_bf16_v5(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
-                      cudaStream_t stream);
 int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream);
-int attention_bf16_v3(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
+int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream);
 
 }  // namespace oasr
