@@ -154,6 +154,13 @@ OASR_API int oasr_profile_read(OasrHandle h, double* ms, int64_t* counts, int32_
 
 /* ---- per-stage entry points (unit parity; all pointers are device pointers) ------------------------- */
 OASR_API int oasr_wave_norm(const float* in, float* out, const int32_t* n_samples_dev, int32_t B, int32_t L, OasrStream stream);
+/* Step before the path (device-side audio front end): interleaved [n_in, channels] fp32 or PCM16 samples at sr_in ->
+ * mono fp32 at sr_out: channel mean + band-limited polyphase resampling with the filter of
+ * torchaudio.functional.resample's defaults (what upstream's host pipeline applies before the model).
+ * out_dev must hold oasr_resample_length(n_in, sr_in, sr_out) = ceil(n_in * sr_out / sr_in) samples. */
+OASR_API int64_t oasr_resample_length(int64_t n_in, int32_t sr_in, int32_t sr_out);
+OASR_API int oasr_resample(const void* in_dev, int32_t in_is_i16, int64_t n_in, int32_t channels, int32_t sr_in,
+                  int32_t sr_out, float* out_dev, int64_t out_capacity, OasrStream stream);
 OASR_API int oasr_fe_layer0(const float* wave, int32_t B, int32_t L, const float* w_10x512, const float* bias,
                    const float* gamma, const float* beta, void* out_bf16 /*[B,T0,512]*/, OasrStream stream);
 /* Stride-2 Conv1d(512->512, k in {2,3}) + bias + LayerNorm(512) + GELU as an implicit GEMM.

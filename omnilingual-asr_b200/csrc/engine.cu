@@ -1101,6 +1101,17 @@ int oasr_wave_norm(const float* in, float* out, const int32_t* n_samples_dev, in
   return rc;
 }
 
+int64_t oasr_resample_length(int64_t n_in, int32_t sr_in, int32_t sr_out) {
+  if (n_in < 0 || sr_in <= 0 || sr_out <= 0) return 0;
+  return resample_length(n_in, sr_in, sr_out);
+}
+
+int oasr_resample(const void* in_dev, int32_t in_is_i16, int64_t n_in, int32_t channels, int32_t sr_in, int32_t sr_out,
+                  float* out_dev, int64_t out_capacity, OasrStream stream) {
+  return resample_mono(in_dev, in_is_i16, n_in, channels, sr_in, sr_out, out_dev, out_capacity,
+                       reinterpret_cast<cudaStream_t>(stream));
+}
+
 int oasr_fe_layer0(const float* wave, int32_t B, int32_t L, const float* w_10x512, const float* bias, const float* gamma,
                    const float* beta, void* out_bf16, OasrStream stream) {
   const int T0 = L >= 10 ? (L - 10) / 5 + 1 : 0;

@@ -15,6 +15,12 @@ int wave_norm(const float* in, float* out, const int* n_samples, int B, int L, l
 int wave_norm_i16(const short* in, float* out, const int* n_samples, int B, int L, long long in_stride,
                   long long out_stride, double* partials, cudaStream_t stream);
 
+// step before the path (resample.cu): interleaved [n_in, channels] fp32 / PCM16 at sr_in -> mono fp32 at sr_out
+// (channel mean + Hann-windowed sinc polyphase filter, torchaudio.functional.resample's defaults)
+long long resample_length(long long n_in, int sr_in, int sr_out);
+int resample_mono(const void* in, int in_is_i16, long long n_in, int channels, int sr_in, int sr_out, float* out,
+                  long long out_capacity, cudaStream_t stream);
+
 // a9: Conv1d(1->512, k=10, s=5) + bias + LayerNorm(512) + GELU -> bf16 channels-last.
 // in [B, L] fp32 (row stride in_stride); out [B, out_rows_stride rows, 512] bf16; T0 = (L-10)/5+1 rows written.
 int fe_layer0(const float* wave, long long in_stride, int B, int L, const float* w /*[10][512]*/, const float* bias,

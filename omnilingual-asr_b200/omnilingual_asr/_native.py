@@ -55,6 +55,8 @@ _PROTOTYPES = {
     "oasr_profile_enable": (C.c_int, [_vp, _i32]),
     "oasr_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64), _i32]),
     "oasr_wave_norm": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "oasr_resample_length": (_i64, [_i64, _i32, _i32]),
+    "oasr_resample": (C.c_int, [_vp, _i32, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
     "oasr_fe_layer0": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_conv_ln_gelu": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_layernorm": (C.c_int, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),

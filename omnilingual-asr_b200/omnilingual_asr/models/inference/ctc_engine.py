@@ -211,6 +211,29 @@ class CtcEngine:
             n_frames=[self.cfg.feature_length(int(v)) for v in n_samples],
             frame_ids=fids[:, :T] if fids is not None else None)
 
+    # ------------------------------------------------------------------ device-side audio front end
+    def resample_to_model_rate(self, samples: np.ndarray | torch.Tensor, sample_rate: int) -> torch.Tensor:
+        """[n] or [n, channels] fp32 / PCM16 samples at `sample_rate` -> mono fp32 DEVICE tensor at 16 kHz
+        (oasr_resample: channel mean + the windowed-sinc filter of torchaudio.functional.resample's defaults)."""
+        from omnilingual_asr.models.config import SAMPLE_RATE
+        if sample_rate <= 0:
+            raise ValueError("sample rate must be positive")
+        t = samples if isinstance(samples, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(samples))
+        if t.dim() == 1:
+            t = t[:, None]
+        if t.dim() != 2 or t.shape[1] > 8:
+            raise ValueError("audio must be [n] or [n, channels] with at most 8 channels")
+        if t.dtype != torch.int16:
+            t = t.to(torch.float32)
+        with self._lock, torch.cuda.device(self.device):
+            t = t.contiguous().to(self.device, non_blocking=True)
+            n_in, ch = int(t.shape[0]), int(t.shape[1])
+            n_out = int(self._lib.oasr_resample_length(n_in, int(sample_rate), SAMPLE_RATE))
+            out = torch.empty((n_out,), dtype=torch.float32, device=self.device)
+            N.check(self._lib.oasr_resample(N.ptr(t), 1 if t.dtype == torch.int16 else 0, n_in, ch, int(sample_rate),
+                                            SAMPLE_RATE, N.ptr(out), n_out, N.stream_ptr()), "oasr_resample")
+        return out
+
     # ------------------------------------------------------------------ debug / accounting
     def debug_forward(self, wave: torch.Tensor, n_samples: Sequence[int], stop_stage: int, *,
                       normalised: bool = False) -> None:

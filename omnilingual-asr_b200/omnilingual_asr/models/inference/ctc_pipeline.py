@@ -23,7 +23,7 @@ from typing import Any, Callable, List, Mapping, Optional, Sequence, Tuple
 import numpy as np
 
 from omnilingual_asr.models.config import SAMPLE_RATE, CtcModelConfig, get_model_config
-from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, shard_range,
+from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, read_wav, shard_range,
                                                     split_into_windows, to_mono_16k)
 from omnilingual_asr.models.inference.tokenizer import CtcVocabulary
 
@@ -81,22 +81,35 @@ class WindowTokens:
 AudioInput = Any  # path | np.ndarray | torch.Tensor | {"waveform": ..., "sample_rate": ...}
 
 
-def _resolve_audio(audio: AudioInput, sample_rate: Optional[int]) -> np.ndarray:
-    """Anything the boundary accepts -> mono float32 at 16 kHz."""
+def _resolve_audio(audio: AudioInput, sample_rate: Optional[int], engine: Any = None):
+    """Anything the boundary accepts -> mono samples at 16 kHz: a host array (float32, or PCM16 left as it is), or -
+    when the audio needs a channel mix or a rate change and the engine has the device-side front end - a float32
+    DEVICE tensor produced by oasr_resample."""
     if isinstance(audio, (str, Path)):
+        p = Path(audio)
+        if engine is not None and hasattr(engine, "resample_to_model_rate") and p.exists() \
+                and p.suffix.lower() in (".wav", ".wave"):
+            x, sr = read_wav(p)
+            return _resolve_audio(x, sr, engine)
         return load_audio_16k(audio)
     if isinstance(audio, Mapping):
-        return _resolve_audio(audio["waveform"], int(audio.get("sample_rate", sample_rate or SAMPLE_RATE)))
+        return _resolve_audio(audio["waveform"], int(audio.get("sample_rate", sample_rate or SAMPLE_RATE)), engine)
     if hasattr(audio, "detach"):  # torch.Tensor
-        audio = audio.detach().cpu().float().numpy()
+        audio = audio.detach().cpu().numpy()
     x = np.asarray(audio)
-    if x.dtype == np.int16 and x.ndim == 1 and int(sample_rate or SAMPLE_RATE) == SAMPLE_RATE:
+    sr = int(sample_rate or SAMPLE_RATE)
+    if x.dtype == np.int16 and x.ndim == 1 and sr == SAMPLE_RATE:
         return x   # mono PCM16 at 16 kHz stays as it is: the device converts it (OASR_FLAG_INPUT_I16)
-    if x.dtype == np.int16:
-        x = x.astype(np.float32) / 32768.0
     if x.ndim == 2 and x.shape[0] < x.shape[1] and x.shape[0] <= 8:
         x = x.T  # [channels, n] -> [n, channels]
-    return to_mono_16k(x, int(sample_rate or SAMPLE_RATE))
+    if x.ndim == 2 and x.shape[1] == 1:
+        x = x[:, 0]
+    needs_front_end = sr != SAMPLE_RATE or x.ndim == 2
+    if needs_front_end and engine is not None and hasattr(engine, "resample_to_model_rate"):
+        return engine.resample_to_model_rate(x, sr)
+    if x.dtype == np.int16:
+        x = x.astype(np.float32) / 32768.0
+    return to_mono_16k(x, sr)
 
 
 class _pinned:
@@ -107,7 +120,8 @@ class _pinned:
 
     def __init__(self, arr: np.ndarray, engine: Any) -> None:
         self.ptr = None
-        if getattr(engine, "device", None) is None or arr.nbytes < self.MIN_BYTES or not arr.flags.c_contiguous:
+        if not isinstance(arr, np.ndarray) or getattr(engine, "device", None) is None or arr.nbytes < self.MIN_BYTES \
+                or not arr.flags.c_contiguous:
             return
         try:
             import torch
@@ -231,10 +245,28 @@ class CTCASRPipeline:
     def _run_windows(self, wave: np.ndarray, windows: List[Tuple[int, int]], lo: int, hi: int) -> List[WindowTokens]:
         """Windows [lo, hi) through the engine in batches; host buffers in, token ids out."""
         out: List[WindowTokens] = []
+        on_device = not isinstance(wave, np.ndarray)      # torch tensor from the device-side front end
         for b0 in range(lo, hi, self.batch_windows):
             idx = list(range(b0, min(hi, b0 + self.batch_windows)))
             L = max(windows[i][1] for i in idx)
             s0 = windows[idx[0]][0]
+            if on_device:
+                contiguous = all(windows[i] == (s0 + r * L, L) for r, i in enumerate(idx))
+                if contiguous:
+                    batch = wave[s0:s0 + len(idx) * L].view(len(idx), L)
+                else:
+                    batch = wave.new_zeros((len(idx), L))
+                    for r, i in enumerate(idx):
+                        s, n = windows[i]
+                        batch[r, :n] = wave[s:s + n]
+                ns = [windows[i][1] for i in idx]
+                with self._lock:
+                    res = self.engine.forward(batch, ns, return_frame_ids=False)
+                for r, i in enumerate(idx):
+                    out.append(WindowTokens(i, windows[i][0], windows[i][1], int(res.n_frames[r]),
+                                            np.asarray(res.token_ids[r], dtype=np.int32),
+                                            np.asarray(res.token_frames[r], dtype=np.int32)))
+                continue
             if all(windows[i] == (s0 + r * L, L) for r, i in enumerate(idx)) and wave.flags.c_contiguous:
                 # full, back-to-back windows: the batch is a [B, L] view of the recording itself (no host copy)
                 batch = wave[s0:s0 + len(idx) * L].reshape(len(idx), L)
@@ -286,7 +318,7 @@ class CTCASRPipeline:
         """One window (<= 40 s), no chunking: GeminiASRPipeline.transcribe (gemini_pipeline.py:474-539)."""
         if progress_callback:
             progress_callback("uploading", 0)
-        wave = _resolve_audio(audio_path, sample_rate)
+        wave = _resolve_audio(audio_path, sample_rate, self.engine)
         return self._transcribe_wave(wave, progress_callback=progress_callback, language=language,
                                      word_timestamps=word_timestamps, chunked=False)
 
@@ -297,7 +329,7 @@ class CTCASRPipeline:
         """Long audio: fixed windows, batched over the device(s), merged in order (gemini_pipeline.py:577-682)."""
         if progress_callback:
             progress_callback("uploading", 0)
-        wave = _resolve_audio(audio_path, sample_rate)
+        wave = _resolve_audio(audio_path, sample_rate, self.engine)
         return self._transcribe_wave(wave, progress_callback=progress_callback, language=language,
                                      word_timestamps=word_timestamps, chunked=True)
 
@@ -310,7 +342,7 @@ class CTCASRPipeline:
         retried: a second attempt cannot change them."""
         if progress_callback:
             progress_callback("uploading", 0)
-        wave = _resolve_audio(audio_path, sample_rate)
+        wave = _resolve_audio(audio_path, sample_rate, self.engine)
         duration = len(wave) / SAMPLE_RATE
         use_chunking = duration > min(MIN_DURATION_FOR_CHUNKING, self.window_samples / SAMPLE_RATE)
         last_error: Optional[BaseException] = None

@@ -259,3 +259,40 @@ def test_pcm16_front_end_equals_host_conversion(device):
     assert (a.frame_ids == b.frame_ids).all()
     assert all((x == y).all() for x, y in zip(a.token_ids, b.token_ids))
     eng.close()
+
+
+def test_config1_file_through_the_device_front_end(device):
+    """gettysburg.wav is 22.05 kHz PCM16: through the drop-in pipeline the file is decoded on the host,
+    mixed / resampled / normalised on the device (oasr_resample + OASR wave_norm); the result must agree with the same
+    pipeline fed the host-resampled 16 kHz waveform (torchaudio filter) - resampling differs at the 1e-6 level."""
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
+    from omnilingual_asr.models.inference.audio import SAMPLE_RATE, read_wav, to_mono_16k
+    import wave as _wave
+    ocfg, w, eng = make_engine("tiny", device)
+    z = np.load(GOLDEN / "gettysburg_16k_i16.npz")
+    # rebuild a 22.05 kHz stereo PCM16 WAV from the committed 16 kHz fixture (the reference file itself is not shipped)
+    base = z["pcm"].astype(np.float32) / 32768.0
+    import torchaudio.functional as AF
+    up = AF.resample(torch.from_numpy(base), 16000, 22050).numpy()
+    pcm = np.clip(up * 32768.0, -32768, 32767).astype(np.int16)
+    stereo = np.stack([pcm, pcm], axis=1)
+    import tempfile, os
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "g.wav")
+        with _wave.open(path, "wb") as wf:
+            wf.setnchannels(2); wf.setsampwidth(2); wf.setframerate(22050); wf.writeframes(stereo.tobytes())
+        pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=5.0, batch_windows=4, distributed=False)
+        a = pipe.transcribe_chunked(path)
+        x, sr = read_wav(path)
+        b = pipe.transcribe_chunked(to_mono_16k(x, sr), sample_rate=SAMPLE_RATE)
+        dev16k = eng.resample_to_model_rate(x, sr).cpu().numpy()
+        host16k = to_mono_16k(x, sr)
+    assert dev16k.shape == host16k.shape and float(np.abs(dev16k - host16k).max()) < 2e-5
+    import difflib
+    ta = " ".join(s.text for s in a.segments)
+    tb = " ".join(s.text for s in b.segments)
+    assert len(a.segments) == len(b.segments) > 0
+    same = difflib.SequenceMatcher(None, ta, tb, autojunk=False).ratio()
+    print(f"device front end vs host resampling: text similarity {same:.4f} over {len(ta)} characters")
+    assert same >= 0.9    # random-init logits are near-ties: a 1e-6 input difference flips a few tokens
+    eng.close()

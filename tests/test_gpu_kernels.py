@@ -368,3 +368,30 @@ def test_outputs_bit_identical_to_rounded_reference(device, gen):
         p = torch.exp2(sl - torch.ceil(sl.amax(-1, keepdim=True)))
         ref = ((p.float().bfloat16().double() @ v) / p.sum(-1, keepdim=True)).permute(0, 2, 1, 3).reshape(Bq * T, d)
         assert same(o, ref) > 0.995
+
+
+# ------------------------------------------------------------------------------------------- device-side front end
+@pytest.mark.parametrize("sr_in,channels,pcm16", [(22050, 1, False), (44100, 2, True), (48000, 1, True), (8000, 1, False),
+                                                  (11025, 2, False), (16000, 2, True)])
+def test_resample_matches_torchaudio(device, gen, sr_in, channels, pcm16):
+    """oasr_resample (channel mean + polyphase windowed sinc) against torchaudio.functional.resample's defaults on the
+    CPU, the filter the host path applies (audio.to_mono_16k); fp32 accumulation order differs: 5e-5 absolute."""
+    import torchaudio.functional as AF
+    n = 50_000 + 37
+    x = torch.randn(n, channels, generator=torch.Generator().manual_seed(5)) * 0.3
+    if pcm16:
+        xi = (x * 32768.0).clamp(-32768, 32767).to(torch.int16)
+        xf = xi.float() / 32768.0
+        src = xi
+    else:
+        xf = x
+        src = x
+    want = AF.resample(xf.mean(dim=1), sr_in, 16000)
+    n_out = int(lib().oasr_resample_length(n, sr_in, 16000))
+    assert n_out == want.numel()
+    d_in = src.contiguous().to(device)
+    out = torch.empty(n_out, dtype=torch.float32, device=device)
+    N.check(lib().oasr_resample(N.ptr(d_in), 1 if pcm16 else 0, n, channels, sr_in, 16000, N.ptr(out), n_out,
+                                N.stream_ptr()), "oasr_resample")
+    sync()
+    assert torch.allclose(out.cpu(), want, atol=5e-5, rtol=0)   # fp32 taps and accumulation on both sides
