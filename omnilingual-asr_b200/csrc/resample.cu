@@ -20,39 +20,56 @@ namespace {
 
 struct ResamplePlan {
   int orig = 0, nw = 0, width = 0, ntaps = 0;
-  float* taps = nullptr;   // [nw][ntaps]
+  float* taps = nullptr;   // [ntaps][nw]
   int* first = nullptr;    // [nw] first input index of the span, relative to frame * orig
 };
 std::map<std::tuple<int, int, int>, ResamplePlan> g_plans;   // (device, orig, new)
 std::mutex g_plan_mu;
 
-__device__ __forceinline__ float sample_at(const float* p, long long i) { return __ldg(p + i); }
-__device__ __forceinline__ float sample_at(const short* p, long long i) { return (float)__ldg(p + i) * (1.0f / 32768.0f); }
+// mono sample i of an interleaved [n, CH] signal (CH = 0: run-time channel count)
+template <int CH>
+__device__ __forceinline__ float mono_at(const float* p, long long i, int channels) {
+  if (CH == 1) return __ldg(p + i);
+  if (CH == 2) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p) + i);
+    return (v.x + v.y) * 0.5f;
+  }
+  float s = 0.f;
+  for (int c = 0; c < channels; ++c) s += __ldg(p + i * channels + c);
+  return s / (float)channels;
+}
+template <int CH>
+__device__ __forceinline__ float mono_at(const short* p, long long i, int channels) {
+  if (CH == 1) return (float)__ldg(p + i) * (1.0f / 32768.0f);
+  if (CH == 2) {
+    const short2 v = __ldg(reinterpret_cast<const short2*>(p) + i);
+    return ((float)v.x * (1.0f / 32768.0f) + (float)v.y * (1.0f / 32768.0f)) * 0.5f;
+  }
+  float s = 0.f;
+  for (int c = 0; c < channels; ++c) s += (float)__ldg(p + i * channels + c) * (1.0f / 32768.0f);
+  return s / (float)channels;
+}
 
-template <typename TIn>
-__global__ void resample_kernel(const TIn* __restrict__ in, long long n_in, int channels, const float* __restrict__ taps,
-                                const int* __restrict__ first, int ntaps, int orig, int nw, float* __restrict__ out,
-                                long long n_out) {
+// One output sample per thread.  Neighbouring threads read overlapping input spans (L1 hits); interior samples take
+// the unchecked loop.
+template <typename TIn, int CH>
+__global__ void __launch_bounds__(256)
+resample_kernel(const TIn* __restrict__ in, long long n_in, int channels, const float* __restrict__ taps,
+                const int* __restrict__ first, int ntaps, int orig, int nw, float* __restrict__ out, long long n_out) {
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n_out) return;
   const long long frame = m / nw;
   const int phase = int(m - frame * nw);
   const long long base = frame * orig + first[phase];
-  const float* h = taps + (long long)phase * ntaps;
-  const float inv_ch = 1.0f / (float)channels;
+  const float* h = taps + phase;   // taps are stored [ntaps][nw]: neighbouring threads = neighbouring phases
   float acc = 0.f;
-  for (int k = 0; k < ntaps; ++k) {
-    const long long i = base + k;
-    if (i >= 0 && i < n_in) {
-      float v;
-      if (channels == 1) {
-        v = sample_at(in, i);
-      } else {
-        float s = 0.f;
-        for (int c = 0; c < channels; ++c) s += sample_at(in, i * channels + c);
-        v = s * inv_ch;
-      }
-      acc = fmaf(v, h[k], acc);
+  if (base >= 0 && base + ntaps <= n_in) {
+#pragma unroll 4
+    for (int k = 0; k < ntaps; ++k) acc = fmaf(mono_at<CH>(in, base + k, channels), __ldg(h + (long long)k * nw), acc);
+  } else {
+    for (int k = 0; k < ntaps; ++k) {
+      const long long i = base + k;
+      if (i >= 0 && i < n_in) acc = fmaf(mono_at<CH>(in, i, channels), __ldg(h + (long long)k * nw), acc);
     }
   }
   out[m] = acc;
@@ -112,7 +129,7 @@ int get_plan(int sr_in, int sr_out, ResamplePlan* out) {
   for (int p = 0; p < nw; ++p) {
     if (hi[p] < lo[p]) continue;
     first[p] = lo[p] - width;
-    for (int k = lo[p]; k <= hi[p]; ++k) taps[(size_t)p * ntaps + (k - lo[p])] = rows[p][k];
+    for (int k = lo[p]; k <= hi[p]; ++k) taps[(size_t)(k - lo[p]) * nw + p] = rows[p][k];
   }
   ResamplePlan pl;
   pl.orig = orig;
@@ -146,12 +163,19 @@ int resample_mono(const void* in, int in_is_i16, long long n_in, int channels, i
   ResamplePlan pl;
   OASR_TRY(get_plan(sr_in, sr_out, &pl));
   const unsigned grid = (unsigned)((n_out + 255) / 256);
-  if (in_is_i16)
-    resample_kernel<short><<<grid, 256, 0, stream>>>(reinterpret_cast<const short*>(in), n_in, channels, pl.taps, pl.first,
-                                                     pl.ntaps, pl.orig, pl.nw, out, n_out);
-  else
-    resample_kernel<float><<<grid, 256, 0, stream>>>(reinterpret_cast<const float*>(in), n_in, channels, pl.taps, pl.first,
-                                                     pl.ntaps, pl.orig, pl.nw, out, n_out);
+#define OASR_RS_LAUNCH(T, CHV)                                                                                       \
+  resample_kernel<T, CHV><<<grid, 256, 0, stream>>>(reinterpret_cast<const T*>(in), n_in, channels, pl.taps, pl.first, \
+                                                    pl.ntaps, pl.orig, pl.nw, out, n_out)
+  if (in_is_i16) {
+    if (channels == 1) OASR_RS_LAUNCH(short, 1);
+    else if (channels == 2) OASR_RS_LAUNCH(short, 2);
+    else OASR_RS_LAUNCH(short, 0);
+  } else {
+    if (channels == 1) OASR_RS_LAUNCH(float, 1);
+    else if (channels == 2) OASR_RS_LAUNCH(float, 2);
+    else OASR_RS_LAUNCH(float, 0);
+  }
+#undef OASR_RS_LAUNCH
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }
