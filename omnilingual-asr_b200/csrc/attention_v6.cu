@@ -9,7 +9,7 @@
 //
 // TMEM columns: S_A S_B S_C (48 each) | P_A P_B P_C (24 used of 32 each) | O_A O_B O_C (head_dim each).
 // Warps: 0-3 / 4-7 / 8-11 softmax + epilogue of tiles A / B / C (warp w owns TMEM lanes [32(w%4), +32)),
-// 12 TMA producer, 13 MMA issuer / TMEM allocator.
+// 12 TMA producer, 13 / 14 / 15 MMA issuers of tiles A / B / C (13 also allocates TMEM).
 #include "host_util.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -22,10 +22,11 @@ namespace oasr {
 namespace {
 
 constexpr int NT = 3;                       // query tiles per CTA
-constexpr int ATT_THREADS = (NT * 4 + 2) * 32;
+constexpr int ATT_THREADS = (NT * 4 + 1 + NT) * 32;
 constexpr int BQ = 128;
 constexpr int MAX_KV_STAGES = 8;
 constexpr int TMEM_COLS = 512;
+constexpr int START_OFFSET_CYCLES = 450;   // tile X issues its first S this many cycles after tile X-1
 constexpr float REF_MARGIN = 80.f;   // a chunk maximum more than 2^80 above the reference moves the reference
 
 __host__ __device__ constexpr int att_bkv(int) { return 48; }
@@ -70,6 +71,7 @@ struct Attn6Params {
   const int* n_frames;
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
+  int start_offset;   // tile X issues its first S this many cycles after tile X-1 (OASR_ATT6_OFFSET overrides)
 };
 constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
 #define ATT_TRACE(role, ev)                                                                                 \
@@ -238,7 +240,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     mbar_init(q_full, 1);
     for (int i = 0; i < MAX_KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], NT);  // one commit per tile's MMA issuer
     }
     for (int i = 0; i < NT; ++i) {
       mbar_init(&s_full[i], 1);
@@ -288,19 +290,24 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         }
       }
     }
-  } else if (warp == NT * 4 + 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    // Warp-uniform control flow; one elected lane issues.  Static order per key block j:
-    //   p_full_B(j-1) -> P.V_B(j-1), release K/V(j-1);  s_free_A(j) -> S_A(j+1);  s_free_B(j) -> S_B(j+1);
-    //   p_full_A(j) -> P.V_A(j)
-    // (the K/V release precedes the wait for block j+1 so that two stages are enough).
+  } else if (warp > NT * 4) {
+    // ---------------------------------------------------------------- MMA issuers: one warp per query tile
+    // Issuing a tcgen05.mma costs the issuing thread ~50-60 cycles and a blocking mbarrier wait ~150 even when its
+    // phase has completed (measured timeline: 5 S-MMAs + commit = 250-400 cycles).  With 48-key blocks a tile needs
+    // 8 MMAs, 2 commits and 3 waits per block, ~900 cycles: one thread cannot serve three tiles inside the ~1150
+    // cycles their exponentials take (a single issuer: ~1900 cycles per block, every tile starved of S for ~750).
+    // Each tile therefore has its own issuing warp; the tiles only meet at the K/V ring (a stage is released by the
+    // commits of all three) and at the start (tile X+1's first S waits until tile X has read its own: the tiles run
+    // a fraction of a block apart).  S_X(j+1) is issued before P.V_X(j) by the same thread, so "s_full(j+2) implies
+    // P.V(j) retired" holds again for the softmax warps' P buffer.
+    const int X = warp - (NT * 4 + 1);
     const bool issuer = elect_one();
     constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     mbar_wait(q_full, 0);
     const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
     const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
-    auto issue_s = [&](int X, int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
+    auto issue_s = [&](int X_, int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
       const uint32_t q_lo = sq_lo + X * (q_tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
       const uint32_t k_lo = skv_lo + st * (2 * kv_tile_bytes >> 4) + (1u << 16);
       const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
@@ -323,7 +330,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     };
     // O_X += P_X V for the V tile in stage st.  V is MN-major: kv rows of 2*VW bytes, 8-row groups SBO = 16*VW
     // apart, the NV column chunks LBO = 2*BKV*VW apart.
-    auto issue_pv = [&](int X, int st, int j) {
+    auto issue_pv = [&](int X_, int st, int j) {
       constexpr uint32_t hi = desc_hi(16 * VW, swz_of(VW));
       const uint32_t v_lo = skv_lo + ((st * 2 * kv_tile_bytes + kv_tile_bytes) >> 4) + (uint32_t((2 * BKV * VW) >> 4) << 16);
       const uint32_t d_tmem = tmem_base + TM_O + X * HD;
@@ -334,59 +341,38 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
           umma_ts(d_tmem, p_tmem + kk * 8, desc64(hi, v_lo + ((kk * 32 * VW) >> 4)), idesc_o, (j | kk) != 0 ? 1u : 0u);
       if (issuer) umma_commit(&o_done[X]);
     };
-    // Static order per key block j, the order of the events when the tiles run a third of a period apart:
-    //   s_free_A(j) -> S_A(j+1);  p_full_C(j-1) -> P.V_C(j-1), release K/V(j-1);  s_free_B(j) -> S_B(j+1);
-    //   p_full_A(j) -> P.V_A(j);  s_free_C(j) -> S_C(j+1);  p_full_B(j) -> P.V_B(j)
-    // In block 0 tile X+1's first S is issued when tile X has read its own: that sets the offsets.  Needs >= 3 K/V
-    // stages (block j+1 is awaited before block j-1 is released).  A polling scheduler (mbarrier.test_wait on all
-    // hand-off barriers, issue whatever is ready) was tried and lost: every test is a ~150-cycle round trip and the
-    // busy warp takes issue slots from the three softmax warps of its sub-partition (profiles/r1_notes.md).
     mbar_wait(&kv_full[0], 0);
+    if (X > 0) {
+      // start the tiles a third of a block period apart, so that the ~430 cycles a softmax warp spends outside its
+      // exponentials per block (P hand-off, TMEM loads) fall into the exponential phases of the other two tiles
+      const long long t_start = clock64();
+      while (clock64() - t_start < (long long)X * p.start_offset) {
+      }
+    }
     tc_fence_after();
-    issue_s(0, 0);
-    int st_prev = 0, st = 0, st_next = 1;
-    uint32_t ph_next = 0u;   // kv_full parity of block j+1
+    issue_s(X, 0);
+    int st = 0, st_next = KS > 1 ? 1 : 0;
+    uint32_t ph_next = KS > 1 ? 0u : 1u;   // kv_full parity of block j+1
     for (int j = 0; j < nblk; ++j) {
-      const bool more = j + 1 < nblk;
-      if (more) mbar_wait(&kv_full[st_next], ph_next);
-      mbar_wait(&s_free[0], j & 1);
-      tc_fence_after();
-      if (j == 0) issue_s(1, 0);
-      if (more) issue_s(0, st_next);
-      if (j > 0) {
-        mbar_wait(&p_full[2], (j - 1) & 1);
+      if (j + 1 < nblk) {
+        mbar_wait(&kv_full[st_next], ph_next);
+        mbar_wait(&s_free[X], j & 1);
         tc_fence_after();
-        issue_pv(2, st_prev, j - 1);
-        if (issuer) umma_commit(&kv_empty[st_prev]);   // K/V of block j-1: every MMA reading them has been issued
-        __syncwarp();
+        issue_s(X, st_next);
+        if (lane == 0 && X == 0) ATT_TRACE(0, j * 2);
       }
-      mbar_wait(&s_free[1], j & 1);
+      mbar_wait(&p_full[X], j & 1);
       tc_fence_after();
-      if (j == 0) issue_s(2, 0);
-      if (more) issue_s(1, st_next);
-      if (lane == 0) ATT_TRACE(0, j * 2);
-      mbar_wait(&p_full[0], j & 1);
-      tc_fence_after();
-      issue_pv(0, st, j);
-      if (lane == 0) ATT_TRACE(0, j * 2 + 1);
-      if (more) {
-        mbar_wait(&s_free[2], j & 1);
-        tc_fence_after();
-        issue_s(2, st_next);
-      }
-      mbar_wait(&p_full[1], j & 1);
-      tc_fence_after();
-      issue_pv(1, st, j);
-      st_prev = st;
+      issue_pv(X, st, j);
+      if (lane == 0 && X == 0) ATT_TRACE(0, j * 2 + 1);
+      if (issuer) umma_commit(&kv_empty[st]);   // K/V of block j: this tile's MMAs reading them have been issued
+      __syncwarp();
       st = st_next;
       if (++st_next == KS) {
         st_next = 0;
         ph_next ^= 1;
       }
     }
-    mbar_wait(&p_full[2], (nblk - 1) & 1);
-    tc_fence_after();
-    issue_pv(2, st_prev, nblk - 1);
   } else {
     // ---------------------------------------------------------------- softmax + epilogue (warps 0-11)
     const int X = warp >> 2;                     // query tile of this warpgroup
@@ -568,6 +554,11 @@ int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.trace = nullptr;
+  static const int start_offset = [] {
+    const char* e = std::getenv("OASR_ATT6_OFFSET");
+    return e != nullptr ? std::atoi(e) : START_OFFSET_CYCLES;
+  }();
+  p.start_offset = start_offset;
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
   if (trace_path != nullptr) {
     OASR_CUDA_CHECK(cudaMalloc(&p.trace, 4 * TRACE_EVENTS * sizeof(long long)));
