@@ -16,7 +16,7 @@
 //
 // TMEM columns: S_A [0,BKV) S_B [BKV,2BKV) P_A, P_B (BKV/2 rounded up to 16 each) O_A, O_B (head_dim each).
 // Warps: 0-3 softmax/epilogue of tile A, 4-7 of tile B (warp w owns TMEM lanes [32(w%4), +32)), 8 TMA producer,
-// 9 MMA issuer / TMEM allocator.
+// 9 / 10 MMA issuers of tiles A / B (9 also allocates TMEM).
 #include "host_util.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -28,7 +28,7 @@
 namespace oasr {
 namespace {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 352;
 constexpr int BQ = 128;
 constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
@@ -76,6 +76,7 @@ struct Attn4Params {
   const int* n_frames;
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
+  int start_offset;   // tile B issues its first S this many cycles after tile A (OASR_ATT4_OFFSET overrides)
 };
 constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (tile A), 2 softmax warp 4 (tile B)
 #define ATT_TRACE(role, ev)                                                                                 \
@@ -244,7 +245,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     mbar_init(q_full, 1);
     for (int i = 0; i < MAX_KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);   // one commit per tile's MMA issuer
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -294,19 +295,23 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         }
       }
     }
-  } else if (warp == 9) {
-    // ---------------------------------------------------------------- MMA issuer
-    // Warp-uniform control flow; one elected lane issues.  Static order per key block j:
-    //   p_full_B(j-1) -> P.V_B(j-1), release K/V(j-1);  s_free_A(j) -> S_A(j+1);  s_free_B(j) -> S_B(j+1);
-    //   p_full_A(j) -> P.V_A(j)
-    // (the K/V release precedes the wait for block j+1 so that two stages are enough).
+  } else if (warp >= 9) {
+    // ---------------------------------------------------------------- MMA issuers: one warp per query tile
+    // Issuing a tcgen05.mma costs the issuing thread ~55 cycles and a blocking mbarrier wait ~150 even when its phase
+    // has completed (stamp trace of the issuing thread, profiles/r1_notes.md).  A tile needs HD/16 + BKV/16 MMAs, two
+    // commits and three waits per key block: ~1100-1200 cycles, so ONE thread serving both tiles took ~2400 cycles
+    // per block - more than the exponentials (1280-1536) - and both tiles starved.  Each tile has its own issuing
+    // warp; they meet only at the K/V ring (a stage is released by both commits).  Tile B starts half a block period
+    // after tile A so that a softmax warp's non-exponential work falls into the other tile's exponentials.  S_X(j+1)
+    // precedes P.V_X(j) on the same thread, so "s_full(j+2) implies P.V(j) retired" holds for the P buffer.
+    const int X = warp - 9;
     const bool issuer = elect_one();
     constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV, 0, 0);
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     mbar_wait(q_full, 0);
     const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
     const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
-    auto issue_s = [&](int X, int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
+    auto issue_s = [&](int X_, int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
       const uint32_t q_lo = sq_lo + X * (q_tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
       const uint32_t k_lo = skv_lo + st * (2 * kv_tile_bytes >> 4) + (1u << 16);
       const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
@@ -329,7 +334,7 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     };
     // O_X += P_X V for the V tile in stage st.  V is MN-major: kv rows of 2*VW bytes, 8-row groups SBO = 16*VW
     // apart, the NV column chunks LBO = 2*BKV*VW apart.
-    auto issue_pv = [&](int X, int st, int j) {
+    auto issue_pv = [&](int X_, int st, int j) {
       constexpr uint32_t hi = desc_hi(16 * VW, swz_of(VW));
       const uint32_t v_lo = skv_lo + ((st * 2 * kv_tile_bytes + kv_tile_bytes) >> 4) + (uint32_t((2 * BKV * VW) >> 4) << 16);
       const uint32_t d_tmem = tmem_base + TM_O + X * HD;
@@ -341,46 +346,35 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       if (issuer) umma_commit(&o_done[X]);
     };
     mbar_wait(&kv_full[0], 0);
+    if (X > 0) {
+      const long long t_start = clock64();
+      while (clock64() - t_start < (long long)p.start_offset) {
+      }
+    }
     tc_fence_after();
-    issue_s(0, 0);
-    int st_prev = 0, st = 0, st_next = KS > 1 ? 1 : 0;
+    issue_s(X, 0);
+    int st = 0, st_next = KS > 1 ? 1 : 0;
     uint32_t ph_next = KS > 1 ? 0u : 1u;   // kv_full parity of block j+1
     for (int j = 0; j < nblk; ++j) {
-      const bool more = j + 1 < nblk;
-      if (j > 0) {
-        mbar_wait(&p_full[1], (j - 1) & 1);
+      if (j + 1 < nblk) {
+        mbar_wait(&kv_full[st_next], ph_next);
+        mbar_wait(&s_free[X], j & 1);
         tc_fence_after();
-        issue_pv(1, st_prev, j - 1);
-        if (issuer) umma_commit(&kv_empty[st_prev]);   // K/V of block j-1: every MMA reading them has been issued
-        __syncwarp();
+        issue_s(X, st_next);
+        if (lane == 0 && X == 0) ATT_TRACE(0, j * 2);
       }
-      if (more) mbar_wait(&kv_full[st_next], ph_next);
-      mbar_wait(&s_free[0], j & 1);
+      mbar_wait(&p_full[X], j & 1);
       tc_fence_after();
-      // Tile B starts when tile A is through the TMEM reads of its first block, so that the exponential phases of
-      // the two softmax warps of an SM sub-partition alternate instead of colliding on the MUFU pipe.
-      if (j == 0) issue_s(1, 0);
-      if (more) {
-        issue_s(0, st_next);
-        mbar_wait(&s_free[1], j & 1);
-        tc_fence_after();
-        issue_s(1, st_next);
-      }
-      if (lane == 0) ATT_TRACE(0, j * 2);
-      mbar_wait(&p_full[0], j & 1);
-      tc_fence_after();
-      issue_pv(0, st, j);
-      if (lane == 0) ATT_TRACE(0, j * 2 + 1);
-      st_prev = st;
+      issue_pv(X, st, j);
+      if (lane == 0 && X == 0) ATT_TRACE(0, j * 2 + 1);
+      if (issuer) umma_commit(&kv_empty[st]);   // K/V of block j: this tile's MMAs reading them have been issued
+      __syncwarp();
       st = st_next;
       if (++st_next == KS) {
         st_next = 0;
         ph_next ^= 1;
       }
     }
-    mbar_wait(&p_full[1], (nblk - 1) & 1);
-    tc_fence_after();
-    issue_pv(1, st_prev, nblk - 1);
   } else {
     // ---------------------------------------------------------------- softmax + epilogue (warps 0-7)
     const int X = warp >> 2;                     // query tile of this warpgroup
@@ -590,6 +584,11 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.trace = nullptr;
+  static const int start_offset = [] {
+    const char* e = std::getenv("OASR_ATT4_OFFSET");
+    return e != nullptr ? std::atoi(e) : 1200;   // half a block period (measured best of 0 / 400 / 800 / 1200)
+  }();
+  p.start_offset = start_offset;
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
   if (trace_path != nullptr) {
     OASR_CUDA_CHECK(cudaMalloc(&p.trace, 3 * TRACE_EVENTS * sizeof(long long)));
