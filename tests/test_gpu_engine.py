@@ -296,3 +296,31 @@ def test_config1_file_through_the_device_front_end(device):
     print(f"device front end vs host resampling: text similarity {same:.4f} over {len(ta)} characters")
     assert same >= 0.9    # random-init logits are near-ties: a 1e-6 input difference flips a few tokens
     eng.close()
+
+
+def test_one_pipeline_shared_by_four_threads(device):
+    """The web app shares ONE pipeline object between up to four worker threads (workflows/wav2elan_web/app.py:38-54,
+    384-389): concurrent transcribe calls must serialise on the handle and return what a lone call returns."""
+    import threading
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
+    ocfg, w, eng = make_engine("tiny", device)
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=3, distributed=False)
+    rng = np.random.default_rng(11)
+    clips = [(rng.standard_normal(16000 * 4 + 123 * i) * 0.2).astype(np.float32) for i in range(4)]
+    want = [[(s.start, s.end, s.text) for s in pipe.transcribe_chunked(c, sample_rate=16000).segments] for c in clips]
+    got = [None] * 4
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = [(s.start, s.end, s.text) for s in pipe.transcribe_chunked(clips[i], sample_rate=16000).segments]
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    assert got == want
+    eng.close()
