@@ -19,6 +19,7 @@
 // 9 / 10 MMA issuers of tiles A / B (9 also allocates TMEM).
 #include "host_util.h"
 #include "kernels.cuh"
+#include "attention_common.cuh"
 #include "ptx.cuh"
 
 #include <cstdlib>
@@ -28,46 +29,14 @@
 namespace oasr {
 namespace {
 
+using namespace att;
+
 constexpr int ATT_THREADS = 352;
 constexpr int BQ = 128;
 constexpr int MAX_KV_STAGES = 4;
 constexpr int TMEM_COLS = 512;
-constexpr float REF_MARGIN = 80.f;   // a chunk maximum more than 2^80 above the reference moves the reference
 
 __host__ __device__ constexpr int att_bkv(int hd) { return hd <= 64 ? 128 : (hd <= 96 ? 96 : 80); }
-__host__ __device__ constexpr int round16(int v) { return (v + 15) & ~15; }
-
-// Column chunks of a [rows][HD] bf16 K-major tile: greedy 64 / 32 / 16 (128B / 64B / 32B swizzle); see v3.
-__host__ __device__ constexpr int qk_nchunks(int hd) {
-  int n = 0;
-  for (int w = 64; w >= 16; w >>= 1)
-    while (hd >= w) {
-      hd -= w;
-      ++n;
-    }
-  return n;
-}
-__host__ __device__ constexpr int qk_w(int hd, int i) {
-  int n = 0;
-  for (int w = 64; w >= 16; w >>= 1)
-    while (hd >= w) {
-      if (n == i) return w;
-      hd -= w;
-      ++n;
-    }
-  return 0;
-}
-__host__ __device__ constexpr int qk_col(int hd, int i) {
-  int c = 0;
-  for (int j = 0; j < i; ++j) c += qk_w(hd, j);
-  return c;
-}
-__host__ __device__ constexpr int v_w(int hd) { return hd % 64 == 0 ? 64 : (hd % 32 == 0 ? 32 : 16); }
-__host__ __device__ constexpr uint32_t swz_of(int w) { return w == 64 ? SWZ_128B : (w == 32 ? SWZ_64B : SWZ_32B); }
-__host__ __device__ constexpr uint32_t desc_hi(int sbo_bytes, uint32_t layout) {
-  return uint32_t((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | ((layout & 7u) << 29);
-}
-__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return (uint64_t(hi) << 32) | lo; }
 
 struct Attn4Params {
   int kv_stages;
@@ -85,113 +54,7 @@ constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (t
       p.trace[(role) * TRACE_EVENTS + (ev)] = clock64();                                                    \
   } while (0)
 
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ uint32_t bf16x2_scale(uint32_t v, uint32_t f2) {
-  uint32_t r;
-  asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(f2));
-  return r;
-}
-
-// 2^x for a packed pair on the FMA pipe (no MUFU): Cody-Waite split with the round-to-nearest magic constant,
-// degree-4 polynomial for 2^f on [-0.5, 0.5] (max relative error 2.7e-6, a 1/1400 of a bf16 ulp), exponent inserted
-// with one integer multiply-add per element.  x must be in [-126, 127].
-__device__ __forceinline__ float2 exp2_fma2(float2 x) {
-  const float2 t = fadd2(x, make_float2(12582912.f, 12582912.f));          // low mantissa bits = round(x)
-  const float2 xi = fadd2(t, make_float2(-12582912.f, -12582912.f));
-  const float2 f = ffma2(xi, make_float2(-1.f, -1.f), x);
-  float2 q = ffma2(make_float2(9.570069611e-03f, 9.570069611e-03f), f, make_float2(5.591785908e-02f, 5.591785908e-02f));
-  q = ffma2(q, f, make_float2(2.402474582e-01f, 2.402474582e-01f));
-  q = ffma2(q, f, make_float2(6.931217909e-01f, 6.931217909e-01f));
-  q = ffma2(q, f, make_float2(9.999992847e-01f, 9.999992847e-01f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
-// Everything a reference move has to touch.
 template <int HD>
-struct RowState {
-  float m_ref;       // integer-valued reference in the log2 domain
-  float sum;         // running sum of the unrounded P of finished blocks
-  float2 sm[2];      // pair-accumulators of the block in flight
-  uint32_t t_o;      // TMEM address of this row's O
-  uint64_t* o_done;  // P.V_X(j) has retired
-  int j;             // key block in flight
-};
-
-// Moves the reference of the rows whose `need` = chunk maximum (log2 domain) - m_ref exceeds REF_MARGIN.  NPK =
-// packed P words of the block computed so far.  Warp-collective (TMEM accesses): called under a warp-uniform branch.
-template <int HD, int NPK, int PKN>
-__device__ __forceinline__ void move_reference(float need, RowState<HD>& rs, uint32_t (&pk)[PKN]) {
-  const float k = need > REF_MARGIN ? ceilf(need) : 0.f;
-  const float f = ex2(-k);   // exact (k is an integer); 0 when the old reference was hopelessly low
-  rs.m_ref += k;
-  rs.sum *= f;
-  rs.sm[0].x *= f; rs.sm[0].y *= f; rs.sm[1].x *= f; rs.sm[1].y *= f;
-  const uint32_t f2 = pack_bf16x2(f, f);
-#pragma unroll
-  for (int i = 0; i < NPK; ++i) pk[i] = bf16x2_scale(pk[i], f2);
-  if (rs.j > 0) {
-    mbar_wait(rs.o_done, (rs.j - 1) & 1);   // P.V(j-1) has finished updating O; P.V(j) cannot start before our p_full
-    tc_fence_after();
-#pragma unroll 1
-    for (int cc = 0; cc < HD; cc += 16) {
-      uint32_t v[16];
-      tmem_ld16(rs.t_o + cc, v);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-      tmem_st16(rs.t_o + cc, v);
-    }
-    tmem_st_wait();
-  }
-}
-
-// W scores of a row (columns [BASE, BASE+W) of the block): reference check, P = 2^(s c - m_ref) -> pk, sums.
-// POLY > 0: every POLY-th pair takes the FMA-pipe exponential instead of MUFU.EX2 (the MUFU pipe is the floor of the
-// kernel: two softmax warps per SM sub-partition cannot issue more than ~1 MUFU per 10 cycles between them).
-template <int HD, int BASE, int W, bool MASKED, int POLY, int PKN>
-__device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, float c, RowState<HD>& rs,
-                                              uint32_t (&pk)[PKN]) {
-  float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
-#pragma unroll
-  for (int i = 0; i < W; ++i)
-    if (!MASKED || BASE + i < ncols) cm4[(i >> 1) & 3] = fmaxf(cm4[(i >> 1) & 3], __uint_as_float(v[i]));
-  const float cm = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
-  if (BASE == 0 && rs.j == 0) {
-    rs.m_ref = ceilf(cm * c);   // first chunk of the row (column 0 is always a valid key)
-  } else {
-    const float need = fmaf(cm, c, -rs.m_ref);
-    if (__any_sync(0xffffffffu, need > REF_MARGIN)) move_reference<HD, BASE / 2>(need, rs, pk);
-  }
-  const float2 c2 = make_float2(c, c), nm2 = make_float2(-rs.m_ref, -rs.m_ref);
-#pragma unroll
-  for (int i = 0; i < W; i += 2) {
-    const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
-    float p0, p1;
-    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-      const float2 e = exp2_fma2(make_float2(fmaxf(x.x, -126.f), fmaxf(x.y, -126.f)));
-      p0 = e.x;
-      p1 = e.y;
-    } else {
-      p0 = ex2(x.x);
-      p1 = ex2(x.y);
-    }
-    if (MASKED) {
-      if (BASE + i >= ncols) p0 = 0.f;
-      if (BASE + i + 1 >= ncols) p1 = 0.f;
-    }
-    rs.sm[(i >> 1) & 1] = fadd2(rs.sm[(i >> 1) & 1], make_float2(p0, p1));
-    pk[(BASE + i) >> 1] = pack_bf16x2(p0, p1);
-  }
-}
-
-template <int HD, int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
@@ -410,8 +273,8 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       // The block is walked in chunks of 32 (16) columns; `full` blocks skip the key mask.
 #define OASR_CHUNK(BASE, W, V)                                                         \
   do {                                                                                 \
-    if (ncols == BKV) softmax_chunk<HD, BASE, W, false, POLY>(V, ncols, c, rs, pk);    \
-    else softmax_chunk<HD, BASE, W, true, POLY>(V, ncols, c, rs, pk);                  \
+    if (ncols == BKV) softmax_chunk<HD, BASE, W, false>(V, ncols, c, rs, pk);    \
+    else softmax_chunk<HD, BASE, W, true>(V, ncols, c, rs, pk);                  \
   } while (0)
       if constexpr (BKV == 128) {
         tmem_ld_wait_on(va);
@@ -596,19 +459,16 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   }
   dim3 grid((T + 2 * BQ - 1) / (2 * BQ), H, B);
   cudaError_t attr_err = cudaSuccess;
-  // POLY (share of exponentials moved to the FMA pipe): measured 587 / 613 / 580 / 568 us for POLY = 0 / 2 / 3 / 4 at the
-  // 1B shape - within run-to-run noise, the softmax warps are issue/latency-bound, not MUFU-bound - so only the plain
-  // MUFU variant is instantiated.
 #define OASR_ATT_CASE(HDV)                                                                                      \
   case HDV: {                                                                                                   \
     static bool attr_done = false;                                                                              \
     if (!attr_done) {                                                                                           \
-      attr_err = cudaFuncSetAttribute(attention_v4_kernel<HDV, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      attr_err = cudaFuncSetAttribute(attention_v4_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       227 * 1024);                                                              \
       attr_done = attr_err == cudaSuccess;                                                                      \
     }                                                                                                           \
     if (attr_err == cudaSuccess)                                                                                \
-      attention_v4_kernel<HDV, 0><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
+      attention_v4_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
                                                                              m.tm[4], m.tm[5], p);              \
     break;                                                                                                      \
   }
