@@ -168,6 +168,38 @@ def test_config1_300m_gettysburg(device):
     eng.close()
 
 
+def test_config2_1b_full_window_against_committed_oracle(device):
+    """The headline model at its real size (BASELINE configs[1], one of the 32 windows): omniASR_CTC_1B, 48 layers,
+    30 s window, against the committed CPU-oracle vector (tests/golden/make_golden_1b.py).  north_star bars: ids 100 %
+    on the fp32-accum check (bf16-operand oracle, frames with a clear top-2 margin), >= 95 % against the fp32 oracle,
+    hidden states within 1e-2 relative."""
+    import bench
+    gold = np.load(GOLDEN / "oracle_1b_window.npz")
+    ocfg = O.PRESETS["omniASR_CTC_1B"]
+    w = O.init_weights(ocfg, seed=0)
+    wave = bench.synthetic_windows(1, 1234)
+    assert hashlib.sha256(wave.numpy().tobytes()).hexdigest() == str(gold["wave_sha256"])
+    eng = CtcEngine(get_model_config("omniASR_CTC_1B"), device=device)
+    eng.load_state_dict(w)
+    del w
+    res = eng.forward(wave.to(device), [wave.shape[1]], normalised=False, return_hidden=True)
+    assert res.n_frames == [1499]
+    ids = res.frame_ids[0]
+    clear = gold["margin_emu"] > NEAR_TIE
+    a_emu = float((ids == gold["ids_emu"]).mean())
+    a_emu_clear = float((ids[clear] == gold["ids_emu"][clear]).mean())
+    a_f32 = float((ids == gold["ids_f32"]).mean())
+    rows = gold["hidden_rows"]
+    hid = res.hidden[0].cpu()[torch.from_numpy(rows).long()]
+    e_emu = rel_err(hid, torch.from_numpy(gold["hidden_emu"]))
+    e_f32 = rel_err(hid, torch.from_numpy(gold["hidden_f32"]))
+    print(f"1B window: ids vs bf16-operand oracle {a_emu:.4f} (margin>{NEAR_TIE}: {a_emu_clear:.4f} on {int(clear.sum())}/1499), "
+          f"vs fp32 oracle {a_f32:.4f}; hidden rel err {e_emu:.2e} / {e_f32:.2e}")
+    assert a_emu_clear >= 0.995 and a_f32 >= 0.95
+    assert e_emu < 1e-2 and e_f32 < 1e-2
+    eng.close()
+
+
 def test_batch_invariance_and_determinism_full_window(device):
     """Size-independent properties at the real window size (30 s, T = 1499) on the 1B architecture with few
     layers: a window's ids do not depend on its batch neighbours, nor on the run."""
