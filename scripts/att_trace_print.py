@@ -1,15 +1,21 @@
-"""Prints the OASR_ATT_TRACE timeline of attention_v4 (CTA 0): per key block and query tile the SM-clock stamps
-start / first two chunks loaded / chunk 0 done / S consumed / all chunks done / P handed over."""
+"""Prints the OASR_ATT_TRACE timeline of the attention kernels (CTA 0).  Rows of the trace file: 0 = MMA-issuing warp of
+tile A (even slots: S issued, odd: P.V issued), 1.. = first softmax warp of tile A, B (, C); per key block j the softmax
+slots are j*6 + {0 block start, 1 S in registers / handed back, 2 first chunk done, 4 all chunks done, 5 P handed over}.
+    OASR_ATT_TRACE=trace.txt python scripts/prof_attention.py 32 1499 16 80 1 ; python scripts/att_trace_print.py trace.txt"""
 import sys
+
 rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
-t0 = min(x for r in rows for x in r if x)
-for role in (1, 2):
-    print("tile", "AB"[role - 1], "(start, ld01, c0, sfree, c12, pdone) relative; deltas; period")
-    r = rows[role]
-    for j in range(0, 20):
-        ev = r[j * 6:(j + 1) * 6]
-        if not ev[0]:
-            break
-        nxt = r[(j + 1) * 6] if (j + 1) * 6 < len(r) else 0
-        print(j, [e - t0 for e in ev], [ev[i + 1] - ev[i] for i in range(5)], (nxt - ev[0]) if nxt else None)
-print("mma (before p_full_A wait, after P.V_A issue):", [(rows[0][2 * j] - t0, rows[0][2 * j + 1] - t0) for j in range(16)])
+t0 = min(x for r in rows for x in r if x > 0)
+tiles = [i for i in range(1, len(rows)) if any(v > 0 for v in rows[i])]
+first = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+for j in range(first, first + 6):
+    parts = []
+    for ti in tiles:
+        r = rows[ti]
+        if (j + 1) * 6 > len(r) or r[j * 6] <= 0:
+            continue
+        ev = [r[j * 6 + k] - t0 if r[j * 6 + k] > 0 else None for k in (0, 1, 2, 4, 5)]
+        parts.append("ABC"[ti - 1] + " " + str(ev))
+    m = rows[0]
+    mma = (m[2 * j] - t0, m[2 * j + 1] - t0) if 2 * j + 1 < len(m) and m[2 * j] > 0 else None
+    print(j, "  ".join(parts), " issuer A (S, P.V):", mma)
