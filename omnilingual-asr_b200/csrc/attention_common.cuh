@@ -65,6 +65,7 @@ struct RowState {
   uint32_t t_o;      // TMEM address of this row's O
   uint64_t* o_done;  // P.V_X(j) has retired
   int j;             // key block in flight
+  uint32_t gb = 0;   // o_done phases completed before block 0 (persistent kernels carry the barrier across work items)
 };
 
 // Moves the reference of the rows whose `need` = chunk maximum (log2 domain) - m_ref exceeds REF_MARGIN.  NPK =
@@ -80,7 +81,7 @@ __device__ __forceinline__ void move_reference(float need, RowState<HD>& rs, uin
 #pragma unroll
   for (int i = 0; i < NPK; ++i) pk[i] = bf16x2_scale(pk[i], f2);
   if (rs.j > 0) {
-    mbar_wait(rs.o_done, (rs.j - 1) & 1);   // P.V(j-1) has finished updating O; P.V(j) cannot start before our p_full
+    mbar_wait(rs.o_done, (rs.gb + rs.j - 1) & 1);   // P.V(j-1) has finished updating O; P.V(j) cannot start before our p_full
     tc_fence_after();
 #pragma unroll 1
     for (int cc = 0; cc < HD; cc += 16) {

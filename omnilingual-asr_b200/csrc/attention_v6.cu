@@ -288,6 +288,7 @@ attention_v6_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       // read latency hides under the P hand-off below
       if (j + 1 < nblk) {
         mbar_wait(&s_full[X], (j + 1) & 1);
+        if (tr) ATT_TRACE(1 + X, j * 6 + 3);
         tc_fence_after();
         tmem_ld32(t_s, va);
         tmem_ld16(t_s + 32, vb);
@@ -407,6 +408,7 @@ int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, in
   const int q_tile_bytes = BQ * hd * 2, kv_tile_bytes = bkv * hd * 2;
   int kv_stages = (227 * 1024 - 2048 - NT * q_tile_bytes) / (2 * kv_tile_bytes);
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
+  if (const char* e = std::getenv("OASR_ATT6_STAGES")) kv_stages = std::atoi(e) < kv_stages ? std::atoi(e) : kv_stages;
   OASR_REQUIRE(kv_stages >= 3, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
   const int smem_bytes = NT * q_tile_bytes + 2 * kv_tile_bytes * kv_stages + 256 + 1024;

@@ -6,7 +6,7 @@ import sys
 
 rows = [list(map(int, l.split())) for l in open(sys.argv[1])]
 t0 = min(x for r in rows for x in r if x > 0)
-tiles = [i for i in range(1, len(rows)) if any(v > 0 for v in rows[i])]
+tiles = [i for i in range(1, min(len(rows), 4)) if any(v > 0 for v in rows[i])]
 first = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 for j in range(first, first + 6):
     parts = []
