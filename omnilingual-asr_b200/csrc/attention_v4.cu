@@ -48,18 +48,26 @@ struct Attn4Params {
   int start_offset;   // tile B issues its first S this many cycles after tile A (OASR_ATT4_OFFSET overrides)
 };
 constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (tile A), 2 softmax warp 4 (tile B)
+// Tracing is a compile-time option (-DOASR_ATT_TRACING): even a never-taken stamp costs the softmax warps issue
+// slots and a dependent parameter load, six times per key block.
+#ifdef OASR_ATT_TRACING
 #define ATT_TRACE(role, ev)                                                                                 \
   do {                                                                                                      \
     if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (ev) < TRACE_EVENTS) \
       p.trace[(role) * TRACE_EVENTS + (ev)] = clock64();                                                    \
   } while (0)
+#else
+#define ATT_TRACE(role, ev) \
+  do {                      \
+  } while (0)
+#endif
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
                     const __grid_constant__ CUtensorMap tmk32, const __grid_constant__ CUtensorMap tmk16,
-                    const Attn4Params p) {
+                    const __grid_constant__ CUtensorMap tmo, const Attn4Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BKV = att_bkv(HD);
@@ -357,22 +365,30 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     tc_fence_after();
     const float inv = 1.0f / rs.sum;
     const int qrow = q0 + X * BQ + r;
-    const bool row_ok = qrow < p.T;
-    __nv_bfloat16* orow = p.out + ((long long)b * p.T + qrow) * p.d + h * HD;
+    // A lane owns a row, and rows are d*2 bytes apart in `out`: direct stores would put 16 bytes into each of 32 lines
+    // per instruction.  The rows go to shared memory instead - into this tile's own Q buffer, which nothing reads any
+    // more once the tile's last P.V has retired (tcgen05.commit covers every earlier MMA of the issuing thread) - and
+    // one TMA store per warp writes its [32 x HD] box; rows >= T are clipped by the tensor map.
+    uint8_t* stage = sQ + X * q_tile_bytes + (warp & 3) * (32 * HD * 2);
 #pragma unroll 1
     for (int cc = 0; cc < HD; cc += 16) {
       uint32_t v[16];
       tmem_ld16(rs.t_o + cc, v);
       tmem_ld_wait();
-      if (row_ok) {
-        uint32_t o[8];
+      uint32_t o[8];
 #pragma unroll
-        for (int i = 0; i < 16; i += 2)
-          o[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-        uint4* dst = reinterpret_cast<uint4*>(orow + cc);
-        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-      }
+      for (int i = 0; i < 16; i += 2)
+        o[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+      uint4* dst = reinterpret_cast<uint4*>(stage + lane * (HD * 2) + cc * 2);
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && qrow < p.T) {   // lane 0 holds the first row of the warp's box
+      tma_store_3d(&tmo, stage, h * HD, qrow, b);
+      bulk_commit_group();
+      bulk_wait_group_read<0>();     // shared memory must outlive the store's read
     }
     tc_fence_before();
   }
@@ -386,9 +402,11 @@ attention_v4_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
 
 struct AttKey {
   const void* base;
+  const void* out;
   int B, T, d3, bkv;
   bool operator<(const AttKey& o) const {
     if (base != o.base) return base < o.base;
+    if (out != o.out) return out < o.out;
     if (B != o.B) return B < o.B;
     if (T != o.T) return T < o.T;
     if (d3 != o.d3) return d3 < o.d3;
@@ -396,7 +414,7 @@ struct AttKey {
   }
 };
 struct AttMaps {
-  CUtensorMap tm[6];
+  CUtensorMap tm[7];
 };
 std::map<AttKey, AttMaps> g_att4_tmaps;
 std::mutex g_att4_mu;
@@ -414,7 +432,7 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   AttMaps m;
   {
     std::lock_guard<std::mutex> g(g_att4_mu);
-    AttKey key{qkv, B, T, 3 * d, bkv};
+    AttKey key{qkv, out, B, T, 3 * d, bkv};
     auto it = g_att4_tmaps.find(key);
     if (it == g_att4_tmaps.end()) {
       uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
@@ -426,6 +444,12 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
         uint32_t kbox[3] = {widths[i], (uint32_t)bkv, 1};
         OASR_TRY(make_tmap_bf16(&m.tm[i], qkv, 3, dims, strides, qbox, swz[i]));
         OASR_TRY(make_tmap_bf16(&m.tm[3 + i], qkv, 3, dims, strides, kbox, swz[i]));
+      }
+      {
+        uint64_t odims[3] = {(uint64_t)d, (uint64_t)T, (uint64_t)B};
+        uint64_t ostrides[2] = {(uint64_t)d * 2, (uint64_t)T * d * 2};
+        uint32_t obox[3] = {(uint32_t)hd, 32, 1};
+        OASR_TRY(make_tmap_bf16(&m.tm[6], out, 3, odims, ostrides, obox, CU_TENSOR_MAP_SWIZZLE_NONE));
       }
       if (g_att4_tmaps.size() > 1024) g_att4_tmaps.clear();
       g_att4_tmaps[key] = m;
@@ -469,7 +493,7 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
     }                                                                                                           \
     if (attr_err == cudaSuccess)                                                                                \
       attention_v4_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
-                                                                             m.tm[4], m.tm[5], p);              \
+                                                                             m.tm[4], m.tm[5], m.tm[6], p);              \
     break;                                                                                                      \
   }
   switch (hd) {

@@ -43,11 +43,19 @@ struct Attn6Params {
   int start_offset;   // tile X issues its first S this many cycles after tile X-1 (OASR_ATT6_OFFSET overrides)
 };
 constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
+// Tracing is a compile-time option (-DOASR_ATT_TRACING): even a never-taken stamp costs the softmax warps issue
+// slots and a dependent parameter load, six times per key block.
+#ifdef OASR_ATT_TRACING
 #define ATT_TRACE(role, ev)                                                                                 \
   do {                                                                                                      \
     if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (ev) < TRACE_EVENTS) \
       p.trace[(role) * TRACE_EVENTS + (ev)] = clock64();                                                    \
   } while (0)
+#else
+#define ATT_TRACE(role, ev) \
+  do {                      \
+  } while (0)
+#endif
 
 template <int HD>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
