@@ -1,6 +1,7 @@
 """Prints the OASR_ATT_TRACE timeline of the attention kernels (CTA 0).  Rows of the trace file: 0 = MMA-issuing warp of
 tile A (even slots: S issued, odd: P.V issued), 1.. = first softmax warp of tile A, B (, C); per key block j the softmax
 slots are j*6 + {0 block start, 1 S in registers / handed back, 2 first chunk done, 4 all chunks done, 5 P handed over}.
+The stamps are compiled in only with `make -C omnilingual-asr_b200/csrc clean all EXTRA=-DOASR_ATT_TRACING` (they cost ~8 %).
     OASR_ATT_TRACE=trace.txt python scripts/prof_attention.py 32 1499 16 80 1 ; python scripts/att_trace_print.py trace.txt"""
 import sys
 
