@@ -85,6 +85,37 @@ def split_into_windows(n_samples: int, window_samples: int) -> List[Tuple[int, i
     return out
 
 
+def split_into_overlapping_windows(n_samples: int, window_samples: int, overlap_samples: int) -> List[Tuple[int, int]]:
+    """Windows of `window_samples` whose starts are `window - overlap` apart (the last one short).  overlap = 0 is the
+    reference law above.  Used with `ownership_bounds`: a window transcribes its whole span but keeps only the tokens
+    of the part it owns, so no word is cut at a window edge."""
+    if overlap_samples <= 0:
+        return split_into_windows(n_samples, window_samples)
+    if overlap_samples >= window_samples:
+        raise ValueError("overlap must be shorter than the window")
+    if n_samples <= 0:
+        return [(0, max(int(n_samples), 0))]
+    hop = window_samples - overlap_samples
+    out = []
+    start = 0
+    while True:
+        out.append((start, min(window_samples, n_samples - start)))
+        if start + window_samples >= n_samples:
+            return out
+        start += hop
+
+
+def ownership_bounds(windows: List[Tuple[int, int]]) -> List[Tuple[float, float]]:
+    """[lo, hi) in samples that each window answers for: neighbours meet in the middle of their overlap; the first
+    window owns from 0, the last to the end.  Without overlap this is every window's own span."""
+    out = []
+    for i, (s, n) in enumerate(windows):
+        lo = 0.0 if i == 0 else (s + (windows[i - 1][0] + windows[i - 1][1])) / 2.0
+        hi = float("inf") if i + 1 == len(windows) else (windows[i + 1][0] + (s + n)) / 2.0
+        out.append((lo, hi))
+    return out
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block partition [lo, hi) of window indices for one rank (merge = concat in rank order)."""
     if world <= 0 or not (0 <= rank < world):

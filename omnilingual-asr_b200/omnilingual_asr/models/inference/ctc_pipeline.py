@@ -23,8 +23,9 @@ from typing import Any, Callable, List, Mapping, Optional, Sequence, Tuple
 import numpy as np
 
 from omnilingual_asr.models.config import SAMPLE_RATE, CtcModelConfig, get_model_config
-from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, read_wav, shard_range,
-                                                    split_into_windows, to_mono_16k)
+from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, ownership_bounds, read_wav,
+                                                    shard_range, split_into_overlapping_windows, split_into_windows,
+                                                    to_mono_16k)
 from omnilingual_asr.models.inference.tokenizer import CtcVocabulary
 
 # Window constants (the reference's CHUNK_DURATION_SECONDS / MIN_DURATION_FOR_CHUNKING / MAX_PARALLEL_CHUNKS,
@@ -179,6 +180,25 @@ def build_segments(win: WindowTokens, vocab: CtcVocabulary, *, word_timestamps: 
     return out
 
 
+def trim_to_ownership(tokens: Sequence[WindowTokens], windows: Sequence[Tuple[int, int]]) -> List[WindowTokens]:
+    """Overlapping windows: keep, per window, the tokens whose frame centre lies in the span the window owns
+    (audio.ownership_bounds).  A frame belongs to exactly one window, so nothing is emitted twice by construction;
+    a token whose peak frame two windows place on different sides of the cut can still be doubled or lost - the cut
+    sits in the middle of the overlap, where both windows have context on either side, to make that rare."""
+    bounds = ownership_bounds(list(windows))
+    out: List[WindowTokens] = []
+    for w in tokens:
+        lo, hi = bounds[w.index]
+        if w.n_frames <= 0 or len(w.token_ids) == 0:
+            out.append(w)
+            continue
+        frame_len = w.n_samples / w.n_frames
+        centre = w.start_sample + (w.token_frames.astype(np.float64) + 0.5) * frame_len
+        keep = (centre >= lo) & (centre < hi)
+        out.append(WindowTokens(w.index, w.start_sample, w.n_samples, w.n_frames, w.token_ids[keep], w.token_frames[keep]))
+    return out
+
+
 def merge_window_results(per_window: Sequence[Tuple[WindowTokens, List[CTCTranscriptSegment]]],
                          language: Optional[str]) -> CTCTranscriptionResult:
     """Sort by window start and concatenate (gemini_pipeline.py:646-678)."""
@@ -200,13 +220,18 @@ class CTCASRPipeline:
                  weights: Any = None, vocabulary: Optional[CtcVocabulary | Sequence[str]] = None,
                  device: Any = None, engine: Any = None, window_seconds: float = CHUNK_DURATION_SECONDS,
                  batch_windows: int = MAX_PARALLEL_CHUNKS, split_gap_sec: Optional[float] = None,
-                 seed: int = 0, distributed: bool = True) -> None:
+                 overlap_seconds: float = 0.0, seed: int = 0, distributed: bool = True) -> None:
         self.cfg = get_model_config(model_card)
         if not (0 < window_seconds <= MAX_ALLOWED_AUDIO_SEC):
             raise ValueError(f"window_seconds must be in (0, {MAX_ALLOWED_AUDIO_SEC}]")
         if batch_windows <= 0:
             raise ValueError("batch_windows must be positive")
         self.window_samples = int(round(window_seconds * SAMPLE_RATE))
+        if not (0 <= overlap_seconds < window_seconds):
+            raise ValueError("overlap_seconds must be in [0, window_seconds)")
+        # 0 = the reference's window law (back-to-back windows).  > 0: consecutive windows share this much audio and
+        # each keeps only the tokens of the part it owns (overlap-and-stitch)
+        self.overlap_samples = int(round(overlap_seconds * SAMPLE_RATE))
         self.batch_windows = int(batch_windows)
         self.split_gap_sec = split_gap_sec
         self.distributed = distributed
@@ -293,7 +318,10 @@ class CTCASRPipeline:
         if not chunked and len(wave) > int(MAX_ALLOWED_AUDIO_SEC * SAMPLE_RATE):
             raise ValueError(f"audio longer than {MAX_ALLOWED_AUDIO_SEC} s needs chunking "
                              "(use transcribe_chunked / transcribe_with_retry)")
-        windows = split_into_windows(len(wave), self.window_samples if chunked else max(len(wave), 1))
+        if chunked and self.overlap_samples > 0:
+            windows = split_into_overlapping_windows(len(wave), self.window_samples, self.overlap_samples)
+        else:
+            windows = split_into_windows(len(wave), self.window_samples if chunked else max(len(wave), 1))
         _report("transcribing", 1)
         rank, world = self._rank_world()
         lo, hi = shard_range(len(windows), rank, world)
@@ -305,6 +333,8 @@ class CTCASRPipeline:
             dist.all_gather_object(gathered, mine)      # host-side gather of token ids only
             mine = [w for part in gathered for w in (part or [])]
         _report("processing", 2)
+        if chunked and self.overlap_samples > 0:
+            mine = trim_to_ownership(mine, windows)
         shaped = [(w, build_segments(w, self.vocab, word_timestamps=word_timestamps,
                                      split_gap_sec=self.split_gap_sec, language=language)) for w in mine]
         result = merge_window_results(shaped, language)

@@ -219,3 +219,44 @@ def test_pcm16_recording_stays_int16_and_full_windows_are_views(engine):
     b = pipe.transcribe_chunked(pcm.astype(np.float32) / 32768.0, sample_rate=16000)
     assert engine.last_dtype == np.float32
     assert [(s.start, s.end, s.text) for s in a.segments] == [(s.start, s.end, s.text) for s in b.segments]
+
+
+def test_overlapping_window_law_and_ownership():
+    from omnilingual_asr.models.inference.audio import ownership_bounds, split_into_overlapping_windows
+    assert split_into_overlapping_windows(100, 40, 0) == [(0, 40), (40, 40), (80, 20)]          # the reference law
+    w = split_into_overlapping_windows(100, 40, 10)
+    assert w == [(0, 40), (30, 40), (60, 40)]                                                     # hop 30, ends at 100
+    assert split_into_overlapping_windows(101, 40, 10)[-1] == (90, 11)
+    assert split_into_overlapping_windows(40, 40, 10) == [(0, 40)]
+    b = ownership_bounds(w)
+    assert b[0] == (0.0, 35.0) and b[1] == (35.0, 65.0) and b[2][0] == 65.0 and b[2][1] == float("inf")
+    with pytest.raises(ValueError):
+        split_into_overlapping_windows(100, 40, 40)
+
+
+def test_overlap_and_stitch_keeps_each_frame_once(engine):
+    """With overlap every window transcribes its whole span, but a token survives only in the window that owns its
+    frame: the kept tokens are exactly the per-window oracle tokens filtered by the ownership bounds."""
+    from omnilingual_asr.models.inference.audio import ownership_bounds, split_into_overlapping_windows
+    import torch
+    wave = noise(2.5, seed=21)
+    engine.calls.clear()
+    pipe = CTCASRPipeline(engine.cfg, engine=engine, window_seconds=1.0, overlap_seconds=0.25, distributed=False)
+    res = pipe.transcribe_chunked(wave, sample_rate=16000, word_timestamps=False)
+    windows = split_into_overlapping_windows(40000, 16000, 4000)
+    assert engine.calls[0][1][0] == 16000 and len(windows) == 3 and windows[1] == (12000, 16000)
+    bounds = ownership_bounds(windows)
+    expect = []
+    for (s, n), (lo, hi) in zip(windows, bounds):
+        x = torch.from_numpy(wave[s:s + n]).float()[None]
+        out = O.forward(engine.w, O.wave_layer_norm(x, [n]), [n], engine.ocfg)
+        ids, frames = O.greedy_collapse(out.frame_ids[0], out.n_frames[0])
+        fl = n / out.n_frames[0]
+        expect += [i for i, f in zip(ids, frames) if lo <= s + (f + 0.5) * fl < hi]
+    got = "".join(seg.text for seg in res.segments)
+    assert got == pipe.vocab.decode(np.array(expect, dtype=np.int32)) or \
+        got.replace(" ", "") == pipe.vocab.decode(np.array(expect, dtype=np.int32)).replace(" ", "")
+    starts = [seg.start for seg in res.segments]
+    assert starts == sorted(starts)
+    with pytest.raises(ValueError):
+        CTCASRPipeline(engine.cfg, engine=engine, window_seconds=1.0, overlap_seconds=1.0)
