@@ -49,6 +49,12 @@ struct GemmKernelParams {
 // CG = CTAs cooperating on one tile (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile with each
 // CTA holding 128 rows of A, half of the B rows and 128 rows of the accumulator.
 constexpr bool epi_has_resid(int epi) { return epi == EPI_F32_RESID || epi == EPI_F32_GELU_RESID; }
+// LayerNorm epilogue with BN = 256: the 512 channels of a row are split over the two CTAs of a cluster (CTA r computes
+// columns [256 r, +256) of the same 128 rows with its own cta_group::1 pipeline), so that each CTA's accumulator is
+// 256 TMEM columns and can be double-buffered: the next tile's MMAs run under the three-pass LayerNorm epilogue, which
+// with a 512-column accumulator had the tensor pipe idle 43 % of the time.  The row statistics are completed through
+// distributed shared memory (each warp writes its partial into both CTAs, one cluster-scope mbarrier per pass).
+constexpr bool epi_nsplit(int bn, int epi) { return epi == EPI_LN_GELU_BF16 && bn == 256; }
 
 template <int BN, int CG, int EPI>
 struct GemmCfg {
@@ -59,7 +65,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
   static constexpr int UMMA_N = BN > 256 ? 256 : BN;
-  static constexpr int BAR_BYTES = 4096;  // barriers (<256 B), LN reduction scratch (2 KB at +256), epilogue barriers (+2304)
+  static constexpr int BAR_BYTES = 5120;  // barriers (<256 B), LN scratch red1 (2 KB at +256), epilogue barriers (+2304), red2 (2 KB at +2560)
   // epilogue staging: per-warp [32][20] word transpose buffers, or (residual epilogues) per warp two 64B-swizzled
   // [32 rows][RES_CW fp32] tiles that TMA fills with the residual and stores back as the output (16 columns: 32 KB
   // in all, which leaves five ring stages; 32-column tiles left four and cost FFN2, K = 5120, 3 %)
@@ -93,7 +99,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const GemmKernelParams p) {
   using C = GemmCfg<BN, CG, EPI>;
-  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  constexpr bool NSPLIT = epi_nsplit(BN, EPI);
+  static_assert(!NSPLIT || CG == 1, "the N-split LayerNorm kernel runs independent cta_group::1 pipelines");
+  const int cluster_rank = (CG == 2 || NSPLIT) ? (int)cluster_ctarank() : 0;
+  const int cta_rank = CG == 2 ? cluster_rank : 0;   // rank within a cta_group::2 pair (row half of the pair tile)
   const bool leader = cta_rank == 0;
   const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -106,7 +115,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* red1 = reinterpret_cast<float*>(bar_base + 256);  // [2][128] LN partial sums
-  float* red2 = red1 + 256;                                // [2][128]
+  float* red2 = reinterpret_cast<float*>(bar_base + 2560); // [2][128]; N-split: red1 / red2 are [cta 2][half 2][128]
+  uint64_t* ln_bar = reinterpret_cast<uint64_t*>(bar_base + 2304);   // N-split: [row quarter 4][pass 2]
   constexpr int STAGE_LD = 20;                             // words per staged row: 16 payload + 4 pad (80 B)
   uint32_t* stage = reinterpret_cast<uint32_t*>(bar_base + C::BAR_BYTES) + ((threadIdx.x >> 5) & 7) * (32 * STAGE_LD);
   float* epi_params = reinterpret_cast<float*>(bar_base + C::BAR_BYTES + C::EPI_STAGE_BYTES);
@@ -130,6 +140,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     if constexpr (epi_has_resid(EPI))
       for (int a = 0; a < EPI_WARPS * 2; ++a) mbar_init(&res_full[a], 1);
+    if constexpr (NSPLIT)
+      for (int a = 0; a < 8; ++a) mbar_init(&ln_bar[a], 4);   // the two column-half warps of either CTA
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -142,7 +154,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised past this point
+  if constexpr (CG == 2 || NSPLIT) cluster_sync_all(); else __syncthreads();   // peer barriers are initialised past this point
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -268,10 +280,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const ulonglong2* wbias2 = reinterpret_cast<const ulonglong2*>(wbias);
     float ln_bias_sum = 0.f;   // IS_LN: sum of the bias over this warp's columns
     if constexpr (IS_LN) {
+      const int col0 = NSPLIT ? cluster_rank * BN : 0;   // N-split: this CTA's 256 of the 512 channels, every tile
       for (int i = (int)threadIdx.x - 128; i < BN; i += EPI_WARPS * 32) {
-        epi_params[i] = __ldg(p.bias + i);
-        epi_params[BN + i] = __ldg(p.ln_gamma + i);
-        epi_params[2 * BN + i] = __ldg(p.ln_beta + i);
+        epi_params[i] = __ldg(p.bias + col0 + i);
+        epi_params[BN + i] = __ldg(p.ln_gamma + col0 + i);
+        epi_params[2 * BN + i] = __ldg(p.ln_beta + col0 + i);
       }
       named_bar_sync(5, EPI_WARPS * 32);
       for (int i = lane; i < HALF_N; i += 32) ln_bias_sum += wbias[i];
@@ -281,6 +294,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int as = 0;
     uint32_t aph = 0;
     const uint32_t tempty_leader0 = CG == 2 ? mapa_u32(smem_u32(&tempty[0]), 0) : 0u;
+    // N-split LayerNorm: the row statistics need the partial sums of four warps, two of them in the peer CTA.  A warp
+    // writes its partial into the same slot of both CTAs, arrives (release.cluster) on the pass's barrier in both, and
+    // waits (acquire.cluster) on its own CTA's: count 4.  Slots are reused a tile later, which the next pass's barrier
+    // orders (a CTA cannot write pass k of tile i+1 before its peer has arrived at pass k' of tile i, after its reads).
+    uint32_t ln_ph = 0;
+    const uint32_t peer_red1 = NSPLIT ? mapa_u32(smem_u32(red1), cluster_rank ^ 1) : 0u;
+    const uint32_t peer_red2 = NSPLIT ? mapa_u32(smem_u32(red2), cluster_rank ^ 1) : 0u;
+    const uint32_t peer_ln_bar = NSPLIT ? mapa_u32(smem_u32(&ln_bar[q * 2]), cluster_rank ^ 1) : 0u;
+    constexpr int LN_N = NSPLIT ? 2 * BN : BN;   // channels of a row
+    auto ln_exchange = [&](float* red, uint32_t peer_red, int pass, float part, int row) -> float {
+      const int slot = (cluster_rank * 2 + half) * 128 + row;
+      red[slot] = part;
+      st_shared_cluster_f32(peer_red + slot * 4, part);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(peer_ln_bar + pass * 8);
+        mbar_arrive(&ln_bar[q * 2 + pass]);
+      }
+      mbar_wait_cluster(&ln_bar[q * 2 + pass], ln_ph);
+      return (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);   // same order in both CTAs
+    };
     // Residual epilogues (out-proj, FFN2, pos-conv) never touch global memory from the epilogue threads: per warp,
     // TMA brings the residual of a [32 rows x 16 columns] chunk into a 64B-swizzled shared tile one chunk ahead
     // (across tile boundaries too), the threads add accumulator + bias (+GELU) in place - row per thread, the TMEM
@@ -403,9 +437,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }, false);
         float sa, sb;
         f2_unpack(f2_add(acc0, acc1), sa, sb);
-        red1[half * 128 + row_in_tile] = sa + sb + ln_bias_sum;
-        named_bar_sync(1 + q, 64);
-        const float mean = (red1[row_in_tile] + red1[128 + row_in_tile]) * (1.0f / BN);
+        float mean;
+        if constexpr (NSPLIT) {
+          mean = ln_exchange(red1, peer_red1, 0, sa + sb + ln_bias_sum, row_in_tile) * (1.0f / LN_N);
+        } else {
+          red1[half * 128 + row_in_tile] = sa + sb + ln_bias_sum;
+          named_bar_sync(1 + q, 64);
+          mean = (red1[row_in_tile] + red1[128 + row_in_tile]) * (1.0f / BN);
+        }
         const f32x2 nmean2 = f2_splat(-mean);
         acc0 = 0ull;
         acc1 = 0ull;
@@ -420,9 +459,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }, false);
         f2_unpack(f2_add(acc0, acc1), sa, sb);
-        red2[half * 128 + row_in_tile] = sa + sb;
-        named_bar_sync(1 + q, 64);
-        const float var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
+        float var;
+        if constexpr (NSPLIT) {
+          var = ln_exchange(red2, peer_red2, 1, sa + sb, row_in_tile) * (1.0f / LN_N);
+          ln_ph ^= 1;
+        } else {
+          red2[half * 128 + row_in_tile] = sa + sb;
+          named_bar_sync(1 + q, 64);
+          var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
+        }
         const f32x2 rstd2 = f2_splat(rsqrtf(var + 1e-5f));
         const ulonglong2* wgamma2 = reinterpret_cast<const ulonglong2*>(wbias + BN);
         const ulonglong2* wbeta2 = reinterpret_cast<const ulonglong2*>(wbias + 2 * BN);
@@ -588,7 +633,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   tc_fence_before();
-  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();   // nobody touches a peer's smem/TMEM past this
+  if constexpr (CG == 2 || NSPLIT) cluster_sync_all(); else __syncthreads();   // nobody touches a peer's smem/TMEM past this
   if (warp == 2) {
     tc_fence_after();
     if constexpr (CG == 2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
@@ -719,11 +764,13 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
                                          C::SMEM_BYTES));
     attr_done = true;
   }
+  constexpr bool NSPLIT = epi_nsplit(BN, EPI);
   const int units = device_sm_count() / CG;   // CTAs or CTA pairs that can be resident
-  const int grid_units = p.total_tiles < units ? p.total_tiles : units;
-  if constexpr (CG == 2) {
+  int grid_units = p.total_tiles < units ? p.total_tiles : units;
+  if (NSPLIT) grid_units &= ~1;   // clusters of two CTAs: tile 2m + r goes to the CTA of rank r (total_tiles is even)
+  if constexpr (CG == 2 || NSPLIT) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid_units * 2);
+    cfg.gridDim = dim3((unsigned)grid_units * CG);
     cfg.blockDim = dim3(GEMM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
@@ -794,6 +841,13 @@ int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
     case EPI_LN_GELU_BF16:
       OASR_REQUIRE(a.N == 512 && a.groups == 1 && a.bias && a.ln_gamma && a.ln_beta,
                    "gemm: LN epilogue needs N == 512 and bias/gamma/beta");
+      {
+        static const bool split = [] {
+          const char* e = std::getenv("OASR_FE_NSPLIT");   // 0: one 512-column accumulator per CTA pair (A/B runs)
+          return e == nullptr || std::atoi(e) != 0;
+        }();
+        if (split) return launch_cg<256, EPI_LN_GELU_BF16, 1>(a, stream);
+      }
       return launch<512, EPI_LN_GELU_BF16>(a, stream);
     default: return fail(OASR_ERR_INVALID, "gemm: unknown epilogue");
   }

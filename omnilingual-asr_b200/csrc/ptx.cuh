@@ -343,6 +343,35 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
 }
 // Same arrive without release semantics: no MEMBAR, so the thread does not wait for its outstanding global stores.
 // Only for hand-offs whose payload is ordered by other means (TMEM reads: tcgen05.wait::ld + fence::before_thread_sync).
+// a float into the shared memory of a CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void st_shared_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// waits on a barrier of this CTA whose arrivals may come from the peer: acquire at cluster scope, so that what the
+// peer wrote into this CTA's shared memory before its (release.cluster) arrive is visible afterwards
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > OASR_MBAR_TIMEOUT_CYCLES) {
+      printf("oasr: cluster mbarrier timeout block %d thread %d bar smem 0x%x parity %u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
