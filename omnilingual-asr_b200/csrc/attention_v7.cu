@@ -554,12 +554,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_qt = (T + NT * BQ - 1) / (NT * BQ);
   OASR_REQUIRE((long long)p.n_qt * H * B < (1ll << 31), "attention: too many work items");
   p.n_items = p.n_qt * H * B;
-  static const int num_sms = [] {
-    int dev = 0, n = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n > 0 ? n : 148;
-  }();
+  const int num_sms = device_sm_count();
   static const int grid_override = [] {
     const char* e = std::getenv("OASR_ATT7_GRID");   // experiments: CTAs to launch (default: one per SM)
     return e != nullptr ? std::atoi(e) : 0;

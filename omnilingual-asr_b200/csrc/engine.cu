@@ -169,8 +169,17 @@ struct OasrEngine {
   size_t tp_off_ln = 0, tp_off_part = 0, tp_off_flags = 0, tp_x_bytes = 0;
   std::vector<void*> tp_peer_base;  // [world], own arena at [rank]
   TpPeerView tp_view{};
+  TpPeerView tp_view2{};            // second flag set (half-batch 1 in overlap mode)
+  unsigned long long tp_epoch2 = 0;
+  cudaStream_t tp_comm_stream2 = nullptr;
+  float* tp_recv2 = nullptr;
   bool tp_fused = false;
   unsigned long long tp_epoch = 0;
+  // overlap mode of the peer-memory path: the reduce kernels run on their own stream beside the other half-batch's GEMMs
+  cudaStream_t tp_comm_stream = nullptr;
+  float* tp_recv = nullptr;         // copy-engine mode: the peers' partial rows of this rank's row share
+  size_t tp_recv_bytes = 0;
+  cudaEvent_t tp_ev_compute[2] = {nullptr, nullptr}, tp_ev_reduce[2] = {nullptr, nullptr};
   // shapes of the last forward (debug buffers)
   int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
   long long last_fe_pad = 0;
@@ -335,6 +344,165 @@ int run_posconv(float* x, int B, int T, int d, int groups, int k, int k_pad, con
   return gemm_bf16_tcgen05(a, st);
 }
 
+// Tensor-parallel encoder layers with the reductions' transfers beside compute (peer-memory path, B >= 2).
+// The batch is cut into two half-batches of windows (attention never crosses a window).  All compute kernels stay on
+// the caller's stream, in the order  P1(h0) P1(h1) P2(h0) P2(h1)  per layer (P1 = QKV, attention, out-proj partial;
+// P2 = FFN1, FFN2 partial).  The all-reduce + residual + LayerNorm of a half-batch (tp_dma_reduce_layernorm: NVLink
+// transfers on the copy engines, a local add + LayerNorm kernel between them) runs on that half-batch's own
+// high-priority stream as soon as its partial sums are complete, i.e. beside the OTHER half-batch's next phase, and
+// the phase that consumes its LayerNorm output waits for it through an event.  Each half-batch has its own flag set,
+// epoch counter and receive buffer.
+int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int stop_stage, cudaStream_t st) {
+  const OasrConfig& c = e->cfg;
+  const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
+  const int W = e->tp_world, d_loc = d / W, F_loc = F / W, H_loc = H / W;
+  const float scale = 1.0f / sqrtf((float)hd);
+  if (e->tp_comm_stream == nullptr) {
+    // highest priority: when an SM frees up between two compute kernels, the (short) reduce work goes first
+    int prio_lo = 0, prio_hi = 0;
+    OASR_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    OASR_CUDA_CHECK(cudaStreamCreateWithPriority(&e->tp_comm_stream, cudaStreamNonBlocking, prio_hi));
+    OASR_CUDA_CHECK(cudaStreamCreateWithPriority(&e->tp_comm_stream2, cudaStreamNonBlocking, prio_hi));
+    for (int i = 0; i < 2; ++i) {
+      OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->tp_ev_compute[i], cudaEventDisableTiming));
+      OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->tp_ev_reduce[i], cudaEventDisableTiming));
+    }
+  }
+  const int Bh[2] = {(B + 1) / 2, B / 2};
+  const int b0[2] = {0, Bh[0]};
+  const long long r0[2] = {0, (long long)Bh[0] * T};
+  const long long Mh[2] = {(long long)Bh[0] * T, (long long)Bh[1] * T};
+  const long long M = Mh[0] + Mh[1];
+  {
+    const long long share = Mh[0] - (Mh[0] / W) * (W - 1);
+    const size_t need = (size_t)(W - 1) * (size_t)share * d * 4;
+    if (need > e->tp_recv_bytes) {   // one buffer per half-batch: their reductions may be in flight together
+      if (e->tp_recv) cudaFree(e->tp_recv);
+      e->tp_recv = nullptr;
+      e->tp_recv_bytes = 0;
+      void* ptr = nullptr;
+      OASR_TRY(dev_alloc(&ptr, 2 * need, false));
+      e->tp_recv = reinterpret_cast<float*>(ptr);
+      e->tp_recv2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ptr) + need);
+      e->tp_recv_bytes = need;
+    }
+  }
+  static const bool timing = std::getenv("OASR_TP_TIMING") != nullptr;
+  static int timing_calls = 0;
+  static cudaEvent_t timing_ev[7] = {};
+  auto reduce_ln = [&](int h, const float* g, const float* bta, bool bcast_x) -> int {
+    // copy-engine mode: each half-batch has its own stream, flag set and receive buffer, so that the transfers of one
+    // reduction run beside the local kernel of the other
+    cudaStream_t cs = h == 1 ? e->tp_comm_stream2 : e->tp_comm_stream;
+    OASR_CUDA_CHECK(cudaEventRecord(e->tp_ev_compute[h], st));
+    OASR_CUDA_CHECK(cudaStreamWaitEvent(cs, e->tp_ev_compute[h], 0));
+    {
+      cudaEvent_t* tr = nullptr;
+      if (timing && ++timing_calls == 9) {   // one call in the steady state of the first forward
+        for (auto& ev : timing_ev) OASR_CUDA_CHECK(cudaEventCreate(&ev));
+        tr = timing_ev;
+        OASR_CUDA_CHECK(cudaEventRecord(timing_ev[6], st));   // the compute stream at the moment the call is issued
+      }
+      if (h == 0) OASR_TRY(tp_dma_reduce_layernorm(e->tp_view, r0[h], Mh[h], d, g, bta, ++e->tp_epoch, bcast_x, e->tp_recv, cs, tr));
+      else OASR_TRY(tp_dma_reduce_layernorm(e->tp_view2, r0[h], Mh[h], d, g, bta, ++e->tp_epoch2, bcast_x, e->tp_recv2, cs, tr));
+    }
+    OASR_CUDA_CHECK(cudaEventRecord(e->tp_ev_reduce[h], cs));
+    return OASR_OK;
+  };
+  bool pending[2] = {false, false};   // a reduce of this half-batch is in flight: its consumer must wait for it
+  auto wait_reduce = [&](int h) -> int {
+    if (pending[h]) OASR_CUDA_CHECK(cudaStreamWaitEvent(st, e->tp_ev_reduce[h], 0));
+    pending[h] = false;
+    return OASR_OK;
+  };
+  prof_mark(e, OASR_PROF_LAYERNORM, st);
+  if (c.n_layers > 0)
+    OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->layers[0].attn_ln_g, e->layers[0].attn_ln_b, e->lnbuf, nullptr, st));
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerW& w = e->layers[l];
+    const bool add_bias = e->tp_first == 0;
+    for (int h = 0; h < 2; ++h) {
+      OASR_TRY(wait_reduce(h));
+      prof_mark(e, OASR_PROF_QKV, st);
+      {
+        GemmArgs a = GemmArgs::plain(e->lnbuf + r0[h] * d, (int)Mh[h], d, d, w.s_wqkv[0], 3 * d_loc);
+        a.bias = w.s_bqkv[0];
+        a.out = e->qkv + r0[h] * 3 * d_loc;
+        a.ldo = 3 * d_loc;
+        a.epilogue = EPI_BF16;
+        OASR_TRY(gemm_bf16_tcgen05(a, st));
+      }
+      prof_mark(e, OASR_PROF_ATTENTION, st);
+      OASR_TRY(attention_bf16(e->qkv + r0[h] * 3 * d_loc, e->att + r0[h] * d_loc, e->n_frames_dev + b0[h], Bh[h], T, H_loc,
+                              hd, scale, st));
+      prof_mark(e, OASR_PROF_OUTPROJ, st);
+      {
+        GemmArgs a = GemmArgs::plain(e->att + r0[h] * d_loc, (int)Mh[h], d_loc, d_loc, w.s_wo[0], d);
+        a.bias = add_bias ? w.bo : nullptr;
+        a.out = e->part + r0[h] * d;
+        a.ldo = d;
+        a.epilogue = EPI_F32;
+        OASR_TRY(gemm_bf16_tcgen05(a, st));
+      }
+      OASR_TRY(reduce_ln(h, w.ffn_ln_g, w.ffn_ln_b, false));
+      pending[h] = true;
+      e->launches += 8;   // 3 compute kernels + signal, wait, local add + LayerNorm, signal, wait
+    }
+    const bool last = l + 1 == c.n_layers;
+    const float* g = last ? e->final_ln_g : e->layers[l + 1].attn_ln_g;
+    const float* bta = last ? e->final_ln_b : e->layers[l + 1].attn_ln_b;
+    const bool want_hidden = last && hidden_out != nullptr;   // parity runs: the fp32 LayerNorm output of all rows
+    for (int h = 0; h < 2; ++h) {
+      OASR_TRY(wait_reduce(h));
+      prof_mark(e, OASR_PROF_FFN1, st);
+      {
+        GemmArgs a = GemmArgs::plain(e->lnbuf + r0[h] * d, (int)Mh[h], d, d, w.s_w1[0], F_loc);
+        a.bias = w.s_b1[0];
+        a.out = e->ffn + r0[h] * F_loc;
+        a.ldo = F_loc;
+        a.epilogue = EPI_BF16_GELU;
+        OASR_TRY(gemm_bf16_tcgen05(a, st));
+      }
+      prof_mark(e, OASR_PROF_FFN2, st);
+      {
+        GemmArgs a = GemmArgs::plain(e->ffn + r0[h] * F_loc, (int)Mh[h], F_loc, F_loc, w.s_w2[0], d);
+        a.bias = add_bias ? w.b2 : nullptr;
+        a.out = e->part + r0[h] * d;
+        a.ldo = d;
+        a.epilogue = EPI_F32;
+        OASR_TRY(gemm_bf16_tcgen05(a, st));
+      }
+      OASR_TRY(reduce_ln(h, g, bta, want_hidden));
+      pending[h] = true;
+      e->launches += 7;
+    }
+    if (stop_stage == 4 + l) {
+      OASR_TRY(wait_reduce(0));
+      OASR_TRY(wait_reduce(1));
+      return OASR_OK;
+    }
+  }
+  OASR_TRY(wait_reduce(0));
+  OASR_TRY(wait_reduce(1));
+  if (timing && timing_calls >= 9 && timing_ev[0] != nullptr) {
+    OASR_CUDA_CHECK(cudaStreamSynchronize(st));
+    OASR_CUDA_CHECK(cudaStreamSynchronize(e->tp_comm_stream));
+    OASR_CUDA_CHECK(cudaStreamSynchronize(e->tp_comm_stream2));
+    float ms[6] = {};
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], timing_ev[i], timing_ev[i + 1]);
+    cudaEventElapsedTime(&ms[5], timing_ev[6], timing_ev[0]);
+    fprintf(stderr, "oasr tp timing (rank %d): issue->start %.3f | ready wait %.3f | dma in %.3f | local %.3f | dma out %.3f | "
+            "done wait %.3f ms\n", e->tp_first, ms[5], ms[0], ms[1], ms[2], ms[3], ms[4]);
+    for (auto& ev : timing_ev) { cudaEventDestroy(ev); ev = nullptr; }
+  }
+  if (hidden_out != nullptr) {
+    prof_mark(e, OASR_PROF_LAYERNORM, st);
+    OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
+  }
+  return OASR_OK;
+}
+
+
 int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const int32_t* n_samples_host, int B, int L,
                  int flags, int stop_stage, float* hidden_out, cudaStream_t st) {
   if (!e->finalized) return fail(OASR_ERR_STATE, "oasr_finalize_weights has not been called");
@@ -438,7 +606,22 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
 
   // a14
   const float scale = 1.0f / sqrtf((float)hd);
-  if (e->tp_world > 1) {
+  // OASR_TP_OVERLAP = dma: the reductions' transfers run on the copy engines beside the other half-batch's GEMMs
+  // (default for two ranks, the configuration verified on hardware) | off: one fused peer-memory kernel per reduction,
+  // nothing beside it (default for more than two ranks)
+  static const int tp_overlap = [] {
+    const char* v = std::getenv("OASR_TP_OVERLAP");
+    if (v == nullptr) return -1;
+    return std::strcmp(v, "dma") == 0 ? 1 : 0;
+  }();
+  const bool overlap = tp_overlap < 0 ? e->tp_world == 2 : tp_overlap == 1;
+  if (e->tp_world > 1 && e->tp_fused && e->tp_local == 1 && B >= 2 && c.n_layers > 0 && overlap) {
+    OASR_TRY(tp_layers_overlapped(e, B, T, hidden_out, stop_stage, st));
+    if (stop_stage >= 4 && stop_stage < 4 + c.n_layers) {
+      prof_mark(e, OASR_PROF_END, st);
+      return OASR_OK;
+    }
+  } else if (e->tp_world > 1) {
     // Tensor-parallel layers: q/k/v + attention + FFN1 on this rank's heads / hidden columns, out-proj and FFN2 as
     // partial sums over the local input columns -> all-reduce -> residual add fused into the next LayerNorm pass.
     const int W = e->tp_world, d_loc = d / W, F_loc = F / W, H_loc = H / W;
@@ -674,6 +857,13 @@ void oasr_destroy(OasrHandle h) {
   for (size_t q = 0; q < h->tp_peer_base.size(); ++q)
     if ((int)q != h->tp_first && h->tp_peer_base[q]) cudaIpcCloseMemHandle(h->tp_peer_base[q]);
   if (h->tp_arena) cudaFree(h->tp_arena);
+  if (h->tp_comm_stream) cudaStreamDestroy(h->tp_comm_stream);
+  if (h->tp_comm_stream2) cudaStreamDestroy(h->tp_comm_stream2);
+  if (h->tp_recv) cudaFree(h->tp_recv);
+  for (int i = 0; i < 2; ++i) {
+    if (h->tp_ev_compute[i]) cudaEventDestroy(h->tp_ev_compute[i]);
+    if (h->tp_ev_reduce[i]) cudaEventDestroy(h->tp_ev_reduce[i]);
+  }
   delete h;
 }
 
@@ -728,7 +918,7 @@ int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out) {
   h->tp_off_ln = up(h->tp_x_bytes);
   h->tp_off_part = h->tp_off_ln + up(M * std::max<size_t>(512, d) * 2);
   h->tp_off_flags = h->tp_off_part + up(M * d * 4);
-  const size_t total = h->tp_off_flags + 256;
+  const size_t total = h->tp_off_flags + 1024;   // two flag sets, 512 B apart (one per half-batch in overlap mode)
   OASR_TRY(dev_alloc(&h->tp_arena, total, true));
   OASR_CUDA_CHECK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t mh;
@@ -765,6 +955,12 @@ int oasr_tp_ipc_import(OasrHandle h, const void* handles) {
     v.done[q] = v.ready[q] + TP_MAX_WORLD;
   }
   v.cta_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(h->tp_arena) + h->tp_off_flags + 2 * TP_MAX_WORLD * 8);
+  h->tp_view2 = v;   // the second flag set: same buffers, flags 512 B further on
+  for (int q = 0; q < W; ++q) {
+    h->tp_view2.ready[q] = v.ready[q] + 64;
+    h->tp_view2.done[q] = v.done[q] + 64;
+  }
+  h->tp_view2.cta_counter = v.cta_counter + 128;
   h->tp_fused = true;
   return OASR_OK;
 }

@@ -53,9 +53,9 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
 template <int MAXJ>
 __global__ void __launch_bounds__(256, 2)
 tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, const float* __restrict__ gamma,
-                    const float* __restrict__ beta, unsigned long long epoch, int bcast_x) {
+                    const float* __restrict__ beta, unsigned long long epoch, int bcast_x, int barriers) {
   // ---- barrier 1: every rank's partial sums are complete
-  if (threadIdx.x == 0) {
+  if (barriers && threadIdx.x == 0) {
     if (blockIdx.x == 0)
       for (int q = 0; q < P.world; ++q) st_release_sys(P.ready[q] + P.rank, epoch);
     for (int q = 0; q < P.world; ++q) spin_until(P.ready[P.rank] + q, epoch);
@@ -63,8 +63,10 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
-  if (r < nrows) {
+  // a warp per row; with a small grid (overlap mode: the CTAs sit on the few SMs the GEMMs leave free) a warp walks
+  // over several rows
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp; r < nrows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const long long row = row0 + r;
     const int ngroups = D >> 2;
     float4 v[MAXJ];
@@ -125,6 +127,7 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
   }
 
   // ---- barrier 2: the last CTA of this rank tells every rank that this rank's rows have landed
+  if (!barriers) return;
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -141,6 +144,14 @@ __global__ void tp_wait_kernel(const unsigned long long* done_flags, int world, 
   if (threadIdx.x < world) spin_until(done_flags + threadIdx.x, epoch);
 }
 
+// thread q tells rank q that this rank has reached `epoch` (flags = P.ready or P.done)
+__global__ void tp_signal_kernel(const TpPeerView P, int which, unsigned long long epoch) {
+  if ((int)threadIdx.x < P.world) {
+    __threadfence_system();
+    st_release_sys((which == 0 ? P.ready[threadIdx.x] : P.done[threadIdx.x]) + P.rank, epoch);
+  }
+}
+
 }  // namespace
 
 int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, const float* gamma, const float* beta,
@@ -150,11 +161,74 @@ int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, 
   const long long row0 = per * P.rank;
   const long long nrows = P.rank == P.world - 1 ? rows_total - row0 : per;
   const unsigned grid = (unsigned)((nrows + 7) / 8 > 0 ? (nrows + 7) / 8 : 1);
-  if (D <= 512) tp_reduce_ln_kernel<4><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0);
-  else if (D <= 1280) tp_reduce_ln_kernel<10><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0);
-  else tp_reduce_ln_kernel<16><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0);
+  if (D <= 512) tp_reduce_ln_kernel<4><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
+  else if (D <= 1280) tp_reduce_ln_kernel<10><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
+  else tp_reduce_ln_kernel<16><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
   // the next kernel on this stream reads LN(x) written by every rank
   tp_wait_kernel<<<1, 32, 0, stream>>>(P.done[P.rank], P.world, epoch);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+// The same reduction with the NVLink transfers on the copy engines, so that no SM time is spent on them and the whole
+// call can run beside GEMMs on another stream (engine.cu: tp_layers_overlapped).  On `stream`, in order:
+//   signal ready -> wait for every rank's ready -> DMA the peers' partial rows of MY row share into `recv`
+//   -> local kernel: x += sum of the partials, LayerNorm -> DMA my LayerNorm rows (and x rows if bcast_x) to every
+//   peer -> signal done -> wait for every rank's done.
+// recv: [(world - 1)][rows_share_max * D] fp32, local.  A peer reads this rank's partial rows between its `ready`
+// wait and its `done` signal, so the caller may overwrite them once this call's stream work has completed.
+int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long rows_total, int D, const float* gamma,
+                            const float* beta, unsigned long long epoch, bool bcast_x, float* recv, cudaStream_t stream,
+                            cudaEvent_t* trace) {
+  OASR_REQUIRE(P.world >= 2 && P.world <= TP_MAX_WORLD && D % 4 == 0 && D <= 2048 && recv != nullptr,
+               "tp_dma: bad arguments");
+  int trace_i = 0;
+  auto stamp = [&]() {   // OASR_TP_TIMING: events between the steps of one call
+    if (trace != nullptr) cudaEventRecord(trace[trace_i++], stream);
+  };
+  stamp();
+  const long long per = rows_total / P.world;
+  const long long row0 = first_row + per * P.rank;
+  const long long nrows = P.rank == P.world - 1 ? rows_total - per * P.rank : per;
+  tp_signal_kernel<<<1, 32, 0, stream>>>(P, 0, epoch);
+  tp_wait_kernel<<<1, 32, 0, stream>>>(P.ready[P.rank], P.world, epoch);
+  stamp();
+  // a view in which every "peer" partial is the local copy the DMA brings in, and LN / x go to local rows only
+  TpPeerView L = P;
+  L.world = P.world;
+  int slot = 0;
+  for (int q = 0; q < P.world; ++q) {
+    L.x[q] = P.x[P.rank];
+    L.ln[q] = P.ln[P.rank];
+    if (q == P.rank) continue;
+    float* dst = recv + (size_t)slot * (size_t)(rows_total - per * (P.world - 1)) * D;   // a slot holds the largest share
+    if (nrows > 0)
+      OASR_CUDA_CHECK(cudaMemcpyAsync(dst, P.part[q] + row0 * D, (size_t)nrows * D * 4, cudaMemcpyDeviceToDevice, stream));
+    L.part[q] = dst - row0 * D;   // the kernel indexes partials by absolute row
+    ++slot;
+  }
+  stamp();
+  if (nrows > 0) {
+    const unsigned grid = (unsigned)((nrows + 7) / 8);
+    // the local view writes each LN row `world` times to the same place; world = 1 for the stores is expressed by
+    // pointing every ln / x entry at the local buffers (idempotent)
+    if (D <= 512) tp_reduce_ln_kernel<4><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else if (D <= 1280) tp_reduce_ln_kernel<10><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else tp_reduce_ln_kernel<16><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    stamp();
+    for (int q = 0; q < P.world; ++q) {
+      if (q == P.rank) continue;
+      OASR_CUDA_CHECK(cudaMemcpyAsync(P.ln[q] + row0 * D, P.ln[P.rank] + row0 * D, (size_t)nrows * D * 2,
+                                      cudaMemcpyDeviceToDevice, stream));
+      if (bcast_x)
+        OASR_CUDA_CHECK(cudaMemcpyAsync(P.x[q] + row0 * D, P.x[P.rank] + row0 * D, (size_t)nrows * D * 4,
+                                        cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  stamp();
+  tp_signal_kernel<<<1, 32, 0, stream>>>(P, 1, epoch);
+  tp_wait_kernel<<<1, 32, 0, stream>>>(P.done[P.rank], P.world, epoch);
+  stamp();
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }

@@ -22,4 +22,9 @@ struct TpPeerView {
 int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, const float* gamma, const float* beta,
                               unsigned long long epoch, bool bcast_x, cudaStream_t stream);
 
+// Same result with the transfers on the copy engines (see tp_fused.cu); recv: (world - 1) * ceil-share rows * D floats.
+int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long rows_total, int D, const float* gamma,
+                            const float* beta, unsigned long long epoch, bool bcast_x, float* recv, cudaStream_t stream,
+                            cudaEvent_t* trace = nullptr);   // trace: 6 events recorded between the steps (timing aid)
+
 }  // namespace oasr
