@@ -446,7 +446,7 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       }
       OASR_TRY(reduce_ln(h, w.ffn_ln_g, w.ffn_ln_b, false));
       pending[h] = true;
-      e->launches += 8;   // 3 compute kernels + signal, wait, local add + LayerNorm, signal, wait
+      e->launches += 6;   // 3 compute kernels + ready signal/wait, local add + LayerNorm, done signal/wait
     }
     const bool last = l + 1 == c.n_layers;
     const float* g = last ? e->final_ln_g : e->layers[l + 1].attn_ln_g;
@@ -474,7 +474,7 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       }
       OASR_TRY(reduce_ln(h, g, bta, want_hidden));
       pending[h] = true;
-      e->launches += 7;
+      e->launches += 5;
     }
     if (stop_stage == 4 + l) {
       OASR_TRY(wait_reduce(0));

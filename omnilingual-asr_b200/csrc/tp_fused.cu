@@ -50,7 +50,10 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int MAXJ>
+// MAXJ: float4 groups of a row per lane (row in registers); AJ: groups of a partial row requested at a time.  The
+// peer-memory launch asks for whole partial rows (AJ = MAXJ: most bytes in flight over NVLink, at the price of spills
+// at D = 2048); the all-local launch of the copy-engine path takes them in two halves and stays within 128 registers.
+template <int MAXJ, int AJ>
 __global__ void __launch_bounds__(256, 2)
 tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, const float* __restrict__ gamma,
                     const float* __restrict__ beta, unsigned long long epoch, int bcast_x, int barriers) {
@@ -78,15 +81,18 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
     }
     for (int q = 0; q < P.world; ++q) {   // partial sums: local and peer rows
       const float4* ps = reinterpret_cast<const float4*>(P.part[q] + row * D);
-      float4 a[MAXJ];
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j)
-        if (lane + 32 * j < ngroups) a[j] = ps[lane + 32 * j];
+      for (int j0 = 0; j0 < MAXJ; j0 += AJ) {
+        float4 a[AJ];
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j)
-        if (lane + 32 * j < ngroups) {
-          v[j].x += a[j].x; v[j].y += a[j].y; v[j].z += a[j].z; v[j].w += a[j].w;
-        }
+        for (int j = 0; j < AJ; ++j)
+          if (j0 + j < MAXJ && lane + 32 * (j0 + j) < ngroups) a[j] = ps[lane + 32 * (j0 + j)];
+#pragma unroll
+        for (int j = 0; j < AJ; ++j)
+          if (j0 + j < MAXJ && lane + 32 * (j0 + j) < ngroups) {
+            v[j0 + j].x += a[j].x; v[j0 + j].y += a[j].y; v[j0 + j].z += a[j].z; v[j0 + j].w += a[j].w;
+          }
+      }
     }
     // The fp32 residual stream stays ROW-SHARDED: only the owner of a row ever adds to it, the other ranks need
     // LN(x) alone (next GEMM's operand), so the new residual row is written locally - unless the caller wants the
@@ -144,11 +150,13 @@ __global__ void tp_wait_kernel(const unsigned long long* done_flags, int world, 
   if (threadIdx.x < world) spin_until(done_flags + threadIdx.x, epoch);
 }
 
-// thread q tells rank q that this rank has reached `epoch` (flags = P.ready or P.done)
-__global__ void tp_signal_kernel(const TpPeerView P, int which, unsigned long long epoch) {
+// thread q tells rank q that this rank has reached `epoch` (which = 0: P.ready, 1: P.done), then waits until rank q
+// has said the same
+__global__ void tp_signal_wait_kernel(const TpPeerView P, int which, unsigned long long epoch) {
   if ((int)threadIdx.x < P.world) {
     __threadfence_system();
     st_release_sys((which == 0 ? P.ready[threadIdx.x] : P.done[threadIdx.x]) + P.rank, epoch);
+    spin_until((which == 0 ? P.ready[P.rank] : P.done[P.rank]) + threadIdx.x, epoch);
   }
 }
 
@@ -161,9 +169,9 @@ int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, 
   const long long row0 = per * P.rank;
   const long long nrows = P.rank == P.world - 1 ? rows_total - row0 : per;
   const unsigned grid = (unsigned)((nrows + 7) / 8 > 0 ? (nrows + 7) / 8 : 1);
-  if (D <= 512) tp_reduce_ln_kernel<4><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
-  else if (D <= 1280) tp_reduce_ln_kernel<10><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
-  else tp_reduce_ln_kernel<16><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
+  if (D <= 512) tp_reduce_ln_kernel<4, 4><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
+  else if (D <= 1280) tp_reduce_ln_kernel<10, 10><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
+  else tp_reduce_ln_kernel<16, 16><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
   // the next kernel on this stream reads LN(x) written by every rank
   tp_wait_kernel<<<1, 32, 0, stream>>>(P.done[P.rank], P.world, epoch);
   OASR_CUDA_CHECK(cudaGetLastError());
@@ -172,7 +180,7 @@ int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, 
 
 // The same reduction with the NVLink transfers on the copy engines, so that no SM time is spent on them and the whole
 // call can run beside GEMMs on another stream (engine.cu: tp_layers_overlapped).  On `stream`, in order:
-//   signal ready -> wait for every rank's ready -> DMA the peers' partial rows of MY row share into `recv`
+//   signal ready + wait for every rank's ready (one kernel) -> DMA the peers' partial rows of MY row share into `recv`
 //   -> local kernel: x += sum of the partials, LayerNorm -> DMA my LayerNorm rows (and x rows if bcast_x) to every
 //   peer -> signal done -> wait for every rank's done.
 // recv: [(world - 1)][rows_share_max * D] fp32, local.  A peer reads this rank's partial rows between its `ready`
@@ -190,8 +198,7 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
   const long long per = rows_total / P.world;
   const long long row0 = first_row + per * P.rank;
   const long long nrows = P.rank == P.world - 1 ? rows_total - per * P.rank : per;
-  tp_signal_kernel<<<1, 32, 0, stream>>>(P, 0, epoch);
-  tp_wait_kernel<<<1, 32, 0, stream>>>(P.ready[P.rank], P.world, epoch);
+  tp_signal_wait_kernel<<<1, 32, 0, stream>>>(P, 0, epoch);
   stamp();
   // a view in which every "peer" partial is the local copy the DMA brings in, and LN / x go to local rows only
   TpPeerView L = P;
@@ -212,9 +219,9 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
     const unsigned grid = (unsigned)((nrows + 7) / 8);
     // the local view writes each LN row `world` times to the same place; world = 1 for the stores is expressed by
     // pointing every ln / x entry at the local buffers (idempotent)
-    if (D <= 512) tp_reduce_ln_kernel<4><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
-    else if (D <= 1280) tp_reduce_ln_kernel<10><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
-    else tp_reduce_ln_kernel<16><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    if (D <= 512) tp_reduce_ln_kernel<4, 2><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else if (D <= 1280) tp_reduce_ln_kernel<10, 5><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else tp_reduce_ln_kernel<16, 8><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
     stamp();
     for (int q = 0; q < P.world; ++q) {
       if (q == P.rank) continue;
@@ -226,8 +233,7 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
     }
   }
   stamp();
-  tp_signal_kernel<<<1, 32, 0, stream>>>(P, 1, epoch);
-  tp_wait_kernel<<<1, 32, 0, stream>>>(P.done[P.rank], P.world, epoch);
+  tp_signal_wait_kernel<<<1, 32, 0, stream>>>(P, 1, epoch);
   stamp();
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
