@@ -155,6 +155,21 @@ struct OasrEngine {
   float* wave_raw = nullptr;        // [B, L] H2D landing buffer of oasr_transcribe_host
   // optional per-stage timing (bench.py): an event at every stage boundary of the forward
   bool profiling = false;
+  // CUDA graphs of the whole forward for small batches (latency path): one per (input buffer, B, L, flags), captured
+  // the second time a shape is seen and replayed from then on, on the engine's own stream
+  struct GraphEntry {
+    const void* wave;
+    long long stride;
+    int B, L, flags;
+    int state;   // 1: seen once (ran eagerly), 2: captured, -1: capture failed, stay eager
+    cudaGraphExec_t exec;
+    long long launches;
+    int last_T, last_fe_idx;
+    long long last_fe_pad;
+  };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t graph_stream = nullptr;
+  cudaEvent_t graph_fork = nullptr, graph_join = nullptr;
   std::vector<std::pair<int, cudaEvent_t>> prof_marks;
   std::vector<cudaEvent_t> prof_pool;
   double prof_ms[OASR_PROF_NCAT] = {};
@@ -226,6 +241,9 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   if (B <= e->ws_B && L <= e->ws_L) return OASR_OK;
   const int nB = std::max(B, e->ws_B), nL = std::max(L, e->ws_L);
   OASR_CUDA_CHECK(cudaDeviceSynchronize());
+  for (auto& g : e->graphs)   // captured graphs hold pointers into the workspace that is about to be replaced
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
   for (void* p : e->ws_owned) cudaFree(p);
   e->ws_owned.clear();
   e->ws_B = e->ws_L = 0;
@@ -503,19 +521,10 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
 }
 
 
-int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const int32_t* n_samples_host, int B, int L,
-                 int flags, int stop_stage, float* hidden_out, cudaStream_t st) {
-  if (!e->finalized) return fail(OASR_ERR_STATE, "oasr_finalize_weights has not been called");
-  OASR_REQUIRE(wave_in && n_samples_host && B > 0 && L > 0, "forward: bad arguments");
+// window lengths -> device (pinned staging slots, so that the copies are asynchronous and a slot is not rewritten
+// before its copy has run)
+int stage_lengths(OasrEngine* e, const int32_t* n_samples_host, int B, int L, cudaStream_t st) {
   const OasrConfig& c = e->cfg;
-  const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
-  OASR_TRY(ensure_workspace(e, B, L));
-  const int T = fe_len(c, L, c.n_fe_layers);
-  const long long M = (long long)B * T;
-  e->last_B = B;
-  e->last_L = L;
-  e->last_T = T;
-
   const int slot = e->stage_next;
   e->stage_next = (slot + 1) % OasrEngine::STAGE_SLOTS;
   if (e->stage_used[slot]) OASR_CUDA_CHECK(cudaEventSynchronize(e->stage_ev[slot]));
@@ -530,6 +539,24 @@ int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const
   if (!e->stage_ev[slot]) OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->stage_ev[slot], cudaEventDisableTiming));
   OASR_CUDA_CHECK(cudaEventRecord(e->stage_ev[slot], st));
   e->stage_used[slot] = true;
+  return OASR_OK;
+}
+
+// staged: the window lengths are already on the device (graph capture / replay: only kernels and device-side
+// memsets follow, nothing that reads host memory)
+int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, const int32_t* n_samples_host, int B, int L,
+                  int flags, int stop_stage, float* hidden_out, bool staged, cudaStream_t st) {
+  if (!e->finalized) return fail(OASR_ERR_STATE, "oasr_finalize_weights has not been called");
+  OASR_REQUIRE(wave_in && n_samples_host && B > 0 && L > 0, "forward: bad arguments");
+  const OasrConfig& c = e->cfg;
+  const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
+  OASR_TRY(ensure_workspace(e, B, L));
+  const int T = fe_len(c, L, c.n_fe_layers);
+  const long long M = (long long)B * T;
+  e->last_B = B;
+  e->last_L = L;
+  e->last_T = T;
+  if (!staged) OASR_TRY(stage_lengths(e, n_samples_host, B, L, st));
 
   // a8
   prof_mark(e, OASR_PROF_WAVE_NORM, st);
@@ -857,6 +884,11 @@ void oasr_destroy(OasrHandle h) {
   for (size_t q = 0; q < h->tp_peer_base.size(); ++q)
     if ((int)q != h->tp_first && h->tp_peer_base[q]) cudaIpcCloseMemHandle(h->tp_peer_base[q]);
   if (h->tp_arena) cudaFree(h->tp_arena);
+  for (auto& g : h->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
+  if (h->graph_fork) cudaEventDestroy(h->graph_fork);
+  if (h->graph_join) cudaEventDestroy(h->graph_join);
   if (h->tp_comm_stream) cudaStreamDestroy(h->tp_comm_stream);
   if (h->tp_comm_stream2) cudaStreamDestroy(h->tp_comm_stream2);
   if (h->tp_recv) cudaFree(h->tp_recv);
@@ -865,6 +897,87 @@ void oasr_destroy(OasrHandle h) {
     if (h->tp_ev_reduce[i]) cudaEventDestroy(h->tp_ev_reduce[i]);
   }
   delete h;
+}
+
+// Small batches are launch-bound (one 30 s window: ~350 launches for ~8 ms of device time): the second time a
+// (buffer, B, L, flags) combination is seen its forward is captured into a CUDA graph and replayed from then on.
+// Capture and replay run on the engine's own stream (the caller's may be the legacy default stream, which cannot be
+// captured), ordered after / before the caller's stream by events.  OASR_GRAPH_MAX_B: largest batch that takes this
+// path (default 8; 0 disables).
+static int forward_impl(OasrEngine* e, const float* wave_in, int64_t wave_stride, const int32_t* n_samples_host, int B,
+                        int L, int flags, int stop_stage, float* hidden_out, cudaStream_t st) {
+  static const int graph_max_b = [] {
+    const char* v = std::getenv("OASR_GRAPH_MAX_B");
+    return v != nullptr ? std::atoi(v) : 8;
+  }();
+  const bool eligible = B > 0 && B <= graph_max_b && L > 0 && stop_stage == 0 && hidden_out == nullptr && !e->profiling &&
+                        e->tp_world == 1 && e->finalized && wave_in != nullptr && n_samples_host != nullptr;
+  if (!eligible) return forward_eager(e, wave_in, wave_stride, n_samples_host, B, L, flags, stop_stage, hidden_out, false, st);
+  OASR_TRY(ensure_workspace(e, B, L));   // before looking anything up: a reallocation drops the captured graphs
+  int gi = -1;
+  for (size_t i = 0; i < e->graphs.size(); ++i) {
+    const auto& g = e->graphs[i];
+    if (g.wave == wave_in && g.stride == wave_stride && g.B == B && g.L == L && g.flags == flags) gi = (int)i;
+  }
+  if (gi < 0) {   // first sight: run eagerly (sets kernel attributes, builds tensor maps)
+    if (e->graphs.size() >= 16) {
+      for (auto& g : e->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+      e->graphs.clear();
+    }
+    e->graphs.push_back({wave_in, (long long)wave_stride, B, L, flags, 1, nullptr, 0, 0, 0, 0});
+    return forward_eager(e, wave_in, wave_stride, n_samples_host, B, L, flags, stop_stage, hidden_out, false, st);
+  }
+  if (e->graphs[gi].state < 0)
+    return forward_eager(e, wave_in, wave_stride, n_samples_host, B, L, flags, stop_stage, hidden_out, false, st);
+  if (e->graph_stream == nullptr) {
+    OASR_CUDA_CHECK(cudaStreamCreateWithFlags(&e->graph_stream, cudaStreamNonBlocking));
+    OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->graph_fork, cudaEventDisableTiming));
+    OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->graph_join, cudaEventDisableTiming));
+  }
+  cudaStream_t gs = e->graph_stream;
+  OASR_CUDA_CHECK(cudaEventRecord(e->graph_fork, st));
+  OASR_CUDA_CHECK(cudaStreamWaitEvent(gs, e->graph_fork, 0));
+  OASR_TRY(stage_lengths(e, n_samples_host, B, L, gs));
+  if (e->graphs[gi].state == 1) {
+    const long long launches0 = e->launches;
+    cudaGraph_t graph = nullptr;
+    OASR_CUDA_CHECK(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+    const int rc = forward_eager(e, wave_in, wave_stride, n_samples_host, B, L, flags, stop_stage, hidden_out, true, gs);
+    const cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc != OASR_OK || ce != cudaSuccess || graph == nullptr ||
+        cudaGraphInstantiate(&exec, graph, nullptr, nullptr, 0) != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();   // clear the capture error; nothing has run yet: fall back to eager launches
+      e->launches = launches0;
+      e->graphs[gi].state = -1;
+      OASR_TRY(forward_eager(e, wave_in, wave_stride, n_samples_host, B, L, flags, stop_stage, hidden_out, true, gs));
+      OASR_CUDA_CHECK(cudaEventRecord(e->graph_join, gs));
+      OASR_CUDA_CHECK(cudaStreamWaitEvent(st, e->graph_join, 0));
+      return OASR_OK;
+    }
+    cudaGraphDestroy(graph);
+    auto& g = e->graphs[gi];
+    g.exec = exec;
+    g.state = 2;
+    g.launches = e->launches - launches0;
+    g.last_T = e->last_T;
+    g.last_fe_idx = e->last_fe_idx;
+    g.last_fe_pad = e->last_fe_pad;
+  } else {
+    const auto& g = e->graphs[gi];
+    e->launches += g.launches;
+    e->last_B = B;
+    e->last_L = L;
+    e->last_T = g.last_T;
+    e->last_fe_idx = g.last_fe_idx;
+    e->last_fe_pad = g.last_fe_pad;
+  }
+  OASR_CUDA_CHECK(cudaGraphLaunch(e->graphs[gi].exec, gs));
+  OASR_CUDA_CHECK(cudaEventRecord(e->graph_join, gs));
+  OASR_CUDA_CHECK(cudaStreamWaitEvent(st, e->graph_join, 0));
+  return OASR_OK;
 }
 
 static int tp_check_split(OasrHandle h, int world) {

@@ -356,3 +356,32 @@ def test_one_pipeline_shared_by_four_threads(device):
     assert not errs, errs
     assert got == want
     eng.close()
+
+
+def test_small_batch_graph_replay_equals_eager_launches(device):
+    """Batches of <= 8 windows are captured into a CUDA graph the second time a (buffer, B, L, flags) combination is
+    seen and replayed afterwards (engine.cu: forward_impl).  The window lengths change between calls - they live in
+    device memory the graph reads - so a replay must give exactly what a first, eagerly launched call gives."""
+    ocfg, w, eng = make_engine("tiny80", device)
+    wave, ns = golden_inputs()
+    B, L = wave.shape
+    assert B <= 8
+    base = wave.to(device)
+    lens = [list(ns), ([L, L // 2, max(L // 3, 400)] + [L] * B)[:B], list(reversed(ns)), list(ns)]
+
+    def windows(n):
+        y = base.clone()
+        for b, k in enumerate(n):
+            y[b, k:] = 0
+        return y
+
+    x = torch.empty_like(base)          # one buffer: call 1 launched eagerly, call 2 captured, calls 3-4 replayed
+    for n in lens:
+        x.copy_(windows(n))
+        g = eng.forward(x, n, return_frame_ids=True)
+        ref = eng.forward(windows(n), n, return_frame_ids=True, return_hidden=True)   # a hidden-state output: never graphed
+        assert list(g.n_frames) == list(ref.n_frames)
+        for b, nf in enumerate(ref.n_frames):
+            assert (g.frame_ids[b, :nf] == ref.frame_ids[b, :nf]).all()
+            assert (np.asarray(g.token_ids[b]) == np.asarray(ref.token_ids[b])).all()
+            assert (np.asarray(g.token_frames[b]) == np.asarray(ref.token_frames[b])).all()
