@@ -180,20 +180,49 @@ def build_segments(win: WindowTokens, vocab: CtcVocabulary, *, word_timestamps: 
     return out
 
 
+def _token_centres(w: WindowTokens) -> np.ndarray:
+    """Absolute sample position of the centre of every token's frame."""
+    if w.n_frames <= 0 or len(w.token_ids) == 0:
+        return np.zeros((0,), dtype=np.float64)
+    return w.start_sample + (w.token_frames.astype(np.float64) + 0.5) * (w.n_samples / w.n_frames)
+
+
+def stitch_bounds(tokens: Sequence[WindowTokens], windows: Sequence[Tuple[int, int]]) -> List[Tuple[float, float]]:
+    """Ownership bounds with every cut moved, inside the overlap of the two windows it separates, to the middle of the
+    longest stretch in which NEITHER window emits a token - a silence both transcriptions agree on - so that the cut
+    does not run through a token one window places just before it and the other just after.  Overlaps without any
+    token, and windows without tokens, keep the geometric middle (audio.ownership_bounds)."""
+    bounds = [list(b) for b in ownership_bounds(list(windows))]
+    by_index = {w.index: w for w in tokens}
+    for i in range(len(windows) - 1):
+        a = float(windows[i + 1][0])                       # the overlap of windows i and i + 1
+        b = float(windows[i][0] + windows[i][1])
+        if b <= a or i not in by_index or i + 1 not in by_index:
+            continue
+        t = np.concatenate([_token_centres(by_index[i]), _token_centres(by_index[i + 1])])
+        t = np.sort(t[(t >= a) & (t < b)])
+        if t.size == 0:
+            continue
+        edges = np.concatenate([[a], t, [b]])
+        k = int(np.argmax(np.diff(edges)))
+        cut = 0.5 * (edges[k] + edges[k + 1])
+        bounds[i][1] = cut
+        bounds[i + 1][0] = cut
+    return [(lo, hi) for lo, hi in bounds]
+
+
 def trim_to_ownership(tokens: Sequence[WindowTokens], windows: Sequence[Tuple[int, int]]) -> List[WindowTokens]:
     """Overlapping windows: keep, per window, the tokens whose frame centre lies in the span the window owns
-    (audio.ownership_bounds).  A frame belongs to exactly one window, so nothing is emitted twice by construction;
-    a token whose peak frame two windows place on different sides of the cut can still be doubled or lost - the cut
-    sits in the middle of the overlap, where both windows have context on either side, to make that rare."""
-    bounds = ownership_bounds(list(windows))
+    (stitch_bounds: neighbours meet in the overlap, at a silence common to both).  A sample position belongs to
+    exactly one window, so nothing is emitted twice by construction."""
+    bounds = stitch_bounds(tokens, windows)
     out: List[WindowTokens] = []
     for w in tokens:
         lo, hi = bounds[w.index]
         if w.n_frames <= 0 or len(w.token_ids) == 0:
             out.append(w)
             continue
-        frame_len = w.n_samples / w.n_frames
-        centre = w.start_sample + (w.token_frames.astype(np.float64) + 0.5) * frame_len
+        centre = _token_centres(w)
         keep = (centre >= lo) & (centre < hi)
         out.append(WindowTokens(w.index, w.start_sample, w.n_samples, w.n_frames, w.token_ids[keep], w.token_frames[keep]))
     return out
