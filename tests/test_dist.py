@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, overlap=0.0):
     for p in (str(ROOT), str(ROOT / "omnilingual-asr_b200")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -25,7 +25,7 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     eng = OracleEngine("tiny")
-    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=2)
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=2, overlap_seconds=overlap)
     x = np.random.default_rng(9).standard_normal(int(5.3 * 16000)).astype(np.float32)
     res = pipe.transcribe_chunked(x)
     windows_here = sum(c[0][0] for c in eng.calls)
@@ -54,3 +54,23 @@ def test_two_rank_shard_and_host_gather(tmp_path):
     assert single == outs[0][0]
     starts = [s[0] for s in single]
     assert starts == sorted(starts)
+
+
+def test_two_rank_overlapping_windows_stitch_after_the_gather(tmp_path):
+    """Overlap-and-stitch needs both neighbours of a cut: it runs after the host gather, on every rank alike."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), 0.25), nprocs=world, join=True)
+    outs = [pickle.load(open(tmp_path / f"r{r}.pkl", "rb")) for r in range(world)]
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] + outs[1][1] == 7                   # 5.3 s in 1 s windows 0.75 s apart
+    for p in (str(ROOT), str(ROOT / "omnilingual-asr_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from omnilingual_asr import CTCASRPipeline
+    from tests._fake_engine import OracleEngine
+    eng = OracleEngine("tiny")
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=2, overlap_seconds=0.25, distributed=False)
+    x = np.random.default_rng(9).standard_normal(int(5.3 * 16000)).astype(np.float32)
+    single = [(s.start, s.end, s.text) for s in pipe.transcribe_chunked(x).segments]
+    assert single == outs[0][0]
