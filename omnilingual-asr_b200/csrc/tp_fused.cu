@@ -13,6 +13,10 @@
 //   done[src]  = e   "src has written its rows of call e everywhere" signalled by the last CTA to finish after a
 //                    system-scope fence, awaited by tp_wait_kernel before the next GEMM of the stream reads LN(x).
 // No kernel waits for a kernel of the SAME GPU; every wait is bounded (trap, not hang).
+//
+// tp_dma_reduce_layernorm (end of this file) is the same reduction with the NVLink transfers on the copy engines and
+// only the add + LayerNorm of this rank's rows on SMs (tp_reduce_ln_kernel on all-local pointers, barriers = 0); the
+// engine runs it on a stream of its own beside the other half-batch's GEMMs (engine.cu: tp_layers_overlapped).
 #include "host_util.h"
 #include "tp_fused.h"
 
