@@ -91,8 +91,9 @@ def split_into_overlapping_windows(n_samples: int, window_samples: int, overlap_
     of the part it owns, so no word is cut at a window edge."""
     if overlap_samples <= 0:
         return split_into_windows(n_samples, window_samples)
-    if overlap_samples >= window_samples:
-        raise ValueError("overlap must be shorter than the window")
+    if 2 * overlap_samples > window_samples:
+        # above half a window the overlaps of (i, i+1) and (i+1, i+2) intersect: a sample could be owned twice
+        raise ValueError("overlap must be at most half the window")
     if n_samples <= 0:
         return [(0, max(int(n_samples), 0))]
     hop = window_samples - overlap_samples

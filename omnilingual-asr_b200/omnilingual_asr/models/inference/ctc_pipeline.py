@@ -195,7 +195,8 @@ def stitch_bounds(tokens: Sequence[WindowTokens], windows: Sequence[Tuple[int, i
     bounds = [list(b) for b in ownership_bounds(list(windows))]
     by_index = {w.index: w for w in tokens}
     for i in range(len(windows) - 1):
-        a = float(windows[i + 1][0])                       # the overlap of windows i and i + 1
+        # the overlap of windows i and i + 1; cuts never cross: the search starts at the previous cut at the earliest
+        a = max(float(windows[i + 1][0]), float(bounds[i][0]))
         b = float(windows[i][0] + windows[i][1])
         if b <= a or i not in by_index or i + 1 not in by_index:
             continue
@@ -256,8 +257,9 @@ class CTCASRPipeline:
         if batch_windows <= 0:
             raise ValueError("batch_windows must be positive")
         self.window_samples = int(round(window_seconds * SAMPLE_RATE))
-        if not (0 <= overlap_seconds < window_seconds):
-            raise ValueError("overlap_seconds must be in [0, window_seconds)")
+        if not (0 <= overlap_seconds <= window_seconds / 2):
+            # above half a window the overlaps of (i, i+1) and (i+1, i+2) intersect and two cuts could cross
+            raise ValueError("overlap_seconds must be in [0, window_seconds / 2]")
         # 0 = the reference's window law (back-to-back windows).  > 0: consecutive windows share this much audio and
         # each keeps only the tokens of the part it owns (overlap-and-stitch)
         self.overlap_samples = int(round(overlap_seconds * SAMPLE_RATE))
@@ -286,15 +288,26 @@ class CTCASRPipeline:
 
     # ------------------------------------------------------------------ device step
     def _rank_world(self) -> Tuple[int, int]:
+        """(data-parallel rank, data-parallel world) of this process.  The ranks of one tensor-parallel group must
+        feed IDENTICAL batches into their shared reductions, so they form one data-parallel replica: with a
+        tensor-parallel engine of degree W the replica index is rank // W of world // W."""
         if not self.distributed:
             return 0, 1
         try:
             import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                return dist.get_rank(), dist.get_world_size()
+            if not (dist.is_available() and dist.is_initialized()):
+                return 0, 1
+            rank, world = dist.get_rank(), dist.get_world_size()
         except Exception:
-            pass
-        return 0, 1
+            return 0, 1
+        tp = int(getattr(self.engine, "tp_world", 1) or 1)
+        if getattr(self.engine, "tp_emulated", False):
+            tp = 1
+        if tp > 1:
+            if world % tp != 0:
+                raise ValueError(f"world size {world} is not a multiple of the engine's tensor-parallel degree {tp}")
+            return rank // tp, world // tp
+        return rank, world
 
     def _run_windows(self, wave: np.ndarray, windows: List[Tuple[int, int]], lo: int, hi: int) -> List[WindowTokens]:
         """Windows [lo, hi) through the engine in batches; host buffers in, token ids out."""
@@ -354,13 +367,28 @@ class CTCASRPipeline:
         _report("transcribing", 1)
         rank, world = self._rank_world()
         lo, hi = shard_range(len(windows), rank, world)
-        with _pinned(wave, self.engine):      # long recordings: page-lock once so that every window copy is a DMA
-            mine = self._run_windows(wave, windows, lo, hi)
+        failure: Optional[BaseException] = None
+        mine: List[WindowTokens] = []
+        try:
+            with _pinned(wave, self.engine):      # long recordings: page-lock once so that every window copy is a DMA
+                mine = self._run_windows(wave, windows, lo, hi)
+        except Exception as e:  # noqa: BLE001 - a failing rank must still take part in the gather below
+            if world <= 1:
+                raise
+            failure = e
         if world > 1:
             import torch.distributed as dist
-            gathered: List[Optional[List[WindowTokens]]] = [None] * world
-            dist.all_gather_object(gathered, mine)      # host-side gather of token ids only
-            mine = [w for part in gathered for w in (part or [])]
+            n_proc = dist.get_world_size()
+            gathered: List[Any] = [None] * n_proc
+            # host-side gather of token ids only; a rank that failed sends a marker instead of leaving the others blocked
+            dist.all_gather_object(gathered, ("error", repr(failure)) if failure is not None else ("ok", mine))
+            bad = [(r, g[1]) for r, g in enumerate(gathered) if g[0] == "error"]
+            if failure is not None:
+                raise failure
+            if bad:
+                raise RuntimeError(f"window shard failed on rank {bad[0][0]}: {bad[0][1]}")
+            tp = n_proc // world               # the ranks of a tensor-parallel group hold the same windows: keep one copy
+            mine = [w for r in range(0, n_proc, tp) for w in gathered[r][1]]
         _report("processing", 2)
         if chunked and self.overlap_samples > 0:
             mine = trim_to_ownership(mine, windows)

@@ -58,6 +58,24 @@ def agreement(ids_gpu, out, margin_floor=None):
     return ok / max(tot, 1), (ok_m / max(tot_m, 1) if margin_floor is not None else None), tot - tot_m
 
 
+MARGINS = (1e-3, 1e-2, NEAR_TIE)
+
+
+def margin_table(ids, gold_ids, gold_margin):
+    """{margin: (frames kept, frames agreeing)} over the frames whose oracle top-2 gap exceeds each margin, plus the
+    unconditional (0.0) row; DESIGN.md section 2 records these counts."""
+    eq = np.asarray(ids) == np.asarray(gold_ids)
+    out = {0.0: (int(eq.size), int(eq.sum()))}
+    for m in MARGINS:
+        keep = np.asarray(gold_margin) > m
+        out[m] = (int(keep.sum()), int(eq[keep].sum()))
+    return out
+
+
+def fmt_table(tab):
+    return ", ".join(f"margin>{m:g}: {ok}/{n}" for m, (n, ok) in tab.items())
+
+
 @pytest.mark.parametrize("name", ["tiny", "tiny80"])
 def test_stagewise_parity(device, name):
     """FE -> projection -> pos-conv -> encoder layers, each against the oracle's taps (emulated operands)."""
@@ -160,11 +178,15 @@ def test_config1_300m_gettysburg(device):
     ref = gold["frame_ids"]
     assert hashlib.sha256(ref.tobytes()).hexdigest() == str(gold["sha256"])
     agree = float((ids == ref).mean())
-    clear = gold["margin"] > 0.05
-    agree_clear = float((ids[clear] == ref[clear]).mean())
-    print(f"300M gettysburg: agreement {agree:.4f}; on margin>0.05 ({int(clear.sum())}/878 frames) {agree_clear:.4f}")
-    assert agree >= 0.95
-    assert agree_clear >= 0.995
+    g2 = np.load(GOLDEN / "oracle_300m_gettysburg_emu.npz")     # both oracle modes + the HF ids (make_golden_fullsize.py)
+    assert (g2["w0_f32_ids"] == ref).mean() > 0.995              # the two fixtures describe the same oracle
+    tab = margin_table(ids, g2["w0_emu_ids"], g2["w0_emu_margin"])
+    a_hf = float((ids == g2["hf_ids"]).mean())
+    print(f"300M gettysburg: vs fp32 oracle {agree:.4f}, vs HF fp32 {a_hf:.4f}; vs bf16-operand oracle {fmt_table(tab)}")
+    assert agree >= 0.95 and a_hf >= 0.95
+    n, ok = tab[NEAR_TIE]
+    assert ok == n                                               # 100 % on the fp32-accum check at the stated margin
+    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0]
     eng.close()
 
 
@@ -195,8 +217,86 @@ def test_config2_1b_full_window_against_committed_oracle(device):
     e_f32 = rel_err(hid, torch.from_numpy(gold["hidden_f32"]))
     print(f"1B window: ids vs bf16-operand oracle {a_emu:.4f} (margin>{NEAR_TIE}: {a_emu_clear:.4f} on {int(clear.sum())}/1499), "
           f"vs fp32 oracle {a_f32:.4f}; hidden rel err {e_emu:.2e} / {e_f32:.2e}")
-    assert a_emu_clear >= 0.995 and a_f32 >= 0.95
+    tab = margin_table(ids, gold["ids_emu"], gold["margin_emu"])
+    print("1B window: vs bf16-operand oracle " + fmt_table(tab))
+    assert a_emu_clear == 1.0 and a_f32 >= 0.95
+    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0]
     assert e_emu < 1e-2 and e_f32 < 1e-2
+    eng.close()
+
+
+def _check_fullsize_window(tag, ids, hidden_rows, g, b):
+    """ids [nf] and hidden rows of window slot b against the committed oracle (both modes) and, for the window that has
+    them, the transformers vectors."""
+    nf = int(g["n_frames"][b])
+    assert len(ids) == nf
+    tab = margin_table(ids, g[f"w{b}_emu_ids"], g[f"w{b}_emu_margin"])
+    a_f32 = float((ids == g[f"w{b}_f32_ids"]).mean())
+    e_emu = rel_err(hidden_rows, torch.from_numpy(g[f"w{b}_emu_hidden"]))
+    e_f32 = rel_err(hidden_rows, torch.from_numpy(g[f"w{b}_f32_hidden"]))
+    msg = f"{tag} window slot {b} ({nf} frames): vs bf16-operand oracle {fmt_table(tab)}; vs fp32 oracle {a_f32:.4f}; " \
+          f"hidden rel err {e_emu:.2e} (emu) / {e_f32:.2e} (fp32)"
+    if int(g["hf_window"]) == b:
+        a_hf = float((ids == g["hf_ids"]).mean())
+        e_hf = rel_err(hidden_rows, torch.from_numpy(g["hf_hidden"]))
+        msg += f"; vs transformers fp32 ids {a_hf:.4f}, hidden {e_hf:.2e}"
+        assert a_hf >= 0.95 and e_hf < 1e-2          # north_star bars against the INDEPENDENT implementation
+    print(msg)
+    n, ok = tab[NEAR_TIE]
+    assert ok == n, msg                              # 100 % on the fp32-accum check at the stated margin
+    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0], msg
+    assert a_f32 >= 0.95 and e_emu < 1e-2 and e_f32 < 1e-2, msg
+
+
+def test_config2_1b_full_depth_batch32(device):
+    """BASELINE configs[1] exactly as benchmarked: omniASR_CTC_1B, 48 layers, the bench batch of 32 x 30 s windows (the
+    last one cut short, so the batch is ragged) through oasr_transcribe_host; windows 0, 13 and 31 against the
+    committed oracle vectors (tests/golden/make_golden_fullsize.py), window 0 also against transformers' fp32 forward."""
+    import bench
+    from tests.golden.make_golden_fullsize import BENCH_SEED, RAGGED_SAMPLES, ROW_STEP
+    g = np.load(GOLDEN / "oracle_1b_batch.npz")
+    wave = bench.synthetic_windows(32, BENCH_SEED)
+    assert hashlib.sha256(wave.numpy().tobytes()).hexdigest() == str(g["bench_batch_sha256"])
+    L = wave.shape[1]
+    ns = [L] * 32
+    ns[31] = RAGGED_SAMPLES
+    wave[31, RAGGED_SAMPLES:] = 0
+    assert [ns[i] for i in g["windows"]] == list(g["n_samples"])
+    eng = CtcEngine(get_model_config("omniASR_CTC_1B"), device=device)
+    eng.load_state_dict(O.init_weights(O.PRESETS["omniASR_CTC_1B"], seed=0))
+    host = eng.transcribe_host(wave.numpy(), ns, return_frame_ids=True)          # the call bench.py's e2e leg times
+    res = eng.forward(wave.to(device), ns, normalised=False, return_hidden=True)
+    assert res.n_frames == [1499] * 31 + [937]
+    assert (host.frame_ids == res.frame_ids).all()                                 # host and device entry points agree
+    for b in range(32):
+        nf = res.n_frames[b]
+        assert (res.frame_ids[b, nf:] == 0).all()
+        want, pos = O.greedy_collapse(host.frame_ids[b], nf)
+        assert host.token_ids[b].tolist() == want and host.token_frames[b].tolist() == pos
+    for slot, widx in enumerate(g["windows"]):
+        nf = int(g["n_frames"][slot])
+        rows = torch.arange(0, nf, ROW_STEP)
+        _check_fullsize_window("1B B=32", host.frame_ids[widx, :nf], res.hidden[widx].cpu()[rows], g, slot)
+    eng.close()
+
+
+def test_config3_3b_full_depth_window(device):
+    """omniASR_CTC_3B at its real depth (60 layers, d 2048, head_dim 128: BASELINE configs[2]'s model), one 30 s
+    window, against the committed oracle vectors and transformers' fp32 forward."""
+    import bench
+    from tests.golden.make_golden_fullsize import BENCH_SEED, ROW_STEP
+    g = np.load(GOLDEN / "oracle_3b_window.npz")
+    wave = bench.synthetic_windows(32, BENCH_SEED)
+    assert hashlib.sha256(wave.numpy().tobytes()).hexdigest() == str(g["bench_batch_sha256"])
+    wave = wave[:1].contiguous()
+    eng = CtcEngine(get_model_config("omniASR_CTC_3B"), device=device)
+    w = O.init_weights(O.PRESETS["omniASR_CTC_3B"], seed=0)
+    eng.load_state_dict(w)
+    del w
+    res = eng.forward(wave.to(device), [wave.shape[1]], normalised=False, return_hidden=True)
+    assert res.n_frames == [1499]
+    rows = torch.arange(0, 1499, ROW_STEP)
+    _check_fullsize_window("3B", res.frame_ids[0, :1499], res.hidden[0].cpu()[rows], g, 0)
     eng.close()
 
 

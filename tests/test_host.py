@@ -287,3 +287,32 @@ def test_stitch_cut_moves_to_the_common_silence():
     e0 = W(0, 0, 100, 10, np.array([5], np.int32), np.array([1], np.int32))
     e1 = W(1, 60, 100, 10, np.array([9], np.int32), np.array([8], np.int32))
     assert P.stitch_bounds([e0, e1], windows)[0][1] == 80.0
+
+
+def test_overlap_above_half_a_window_is_rejected_and_half_is_safe(engine):
+    """Above half a window the overlaps of (i, i+1) and (i+1, i+2) intersect and two cuts could cross:
+    rejected at construction and by the window law.  At exactly half a window every sample still has one owner: the
+    cuts are non-decreasing and no token is kept twice."""
+    from omnilingual_asr.models.inference.audio import split_into_overlapping_windows
+    with pytest.raises(ValueError):
+        CTCASRPipeline(engine.cfg, engine=engine, window_seconds=1.0, overlap_seconds=0.75)
+    with pytest.raises(ValueError):
+        split_into_overlapping_windows(100, 40, 30)
+    W = P.WindowTokens
+    windows = split_into_overlapping_windows(100, 40, 20)      # starts 0, 20, 40, 60: overlaps [20,40) [40,60) [60,80)
+    assert windows == [(0, 40), (20, 40), (40, 40), (60, 40)]
+    rng = np.random.default_rng(5)
+    toks = []
+    for i, (s0, n) in enumerate(windows):                      # 40 frames of one sample; random tokens everywhere
+        frames = np.sort(rng.choice(40, size=12, replace=False)).astype(np.int32)
+        toks.append(W(i, s0, n, 40, rng.integers(1, 9, size=12).astype(np.int32), frames))
+    bounds = P.stitch_bounds(toks, windows)
+    cuts = [b[1] for b in bounds[:-1]]
+    assert cuts == sorted(cuts) and all(bounds[i][1] == bounds[i + 1][0] for i in range(3))
+    kept = P.trim_to_ownership(toks, windows)
+    centres = np.concatenate([P._token_centres(w) for w in kept])
+    owners = np.concatenate([np.full(len(w.token_ids), w.index) for w in kept])
+    for c, o in zip(centres, owners):                          # every kept token lies in its owner's span only
+        lo, hi = bounds[o]
+        assert lo <= c < hi
+        assert sum(1 for (l2, h2) in bounds if l2 <= c < h2) == 1

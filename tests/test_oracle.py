@@ -124,3 +124,41 @@ def test_config1_oracle_reproduces_golden_ids():
     agree = (ids == gold["frame_ids"])
     assert agree[gold["margin"] > 1e-3].all()
     assert agree.mean() > 0.995
+
+
+@pytest.mark.parametrize("fixture,bound", [("oracle_1b_batch.npz", 1e-4), ("oracle_3b_window.npz", 2e-4),
+                                           ("oracle_300m_gettysburg_emu.npz", 1e-4)])
+def test_fullsize_hf_pins_recorded(fixture, bound):
+    """What tests/golden/make_golden_fullsize.py measured when it ran transformers' Wav2Vec2ForCTC (fp32, the oracle's
+    weights) at the REAL model sizes: oracle(fp32) and HF agree to fp32 round-off in logits and hidden states, and on
+    every frame id outside exact near-ties."""
+    g = np.load(GOLDEN / fixture)
+    assert float(g["hf_max_abs_dlogit"]) < bound and float(g["hf_max_abs_dhidden"]) < bound
+    b = int(g["hf_window"])
+    flips = np.nonzero(g["hf_ids"] != g[f"w{b}_f32_ids"])[0]
+    assert len(flips) <= 2 and all(g[f"w{b}_f32_margin"][t] < 2 * bound for t in flips)
+    assert np.abs(g["hf_hidden"] - g[f"w{b}_f32_hidden"]).max() < bound
+    # the bf16-operand mode stays within the north_star bars of the fp32 mode at full size
+    assert float((g[f"w{b}_emu_ids"] == g[f"w{b}_f32_ids"]).mean()) >= 0.95
+
+
+@pytest.mark.slow
+def test_fullsize_1b_window_oracle_reproduces_hf_vectors():
+    """Live: today's fp32 oracle on one full 30 s window of omniASR_CTC_1B (48 layers, T = 1499; ~30 s of CPU) against
+    the stored transformers vectors - the full-size pin does not depend on the oracle that wrote the fixture."""
+    import bench
+    from tests.golden.make_golden_fullsize import BENCH_SEED, ROW_STEP
+    g = np.load(GOLDEN / "oracle_1b_batch.npz")
+    cfg = O.PRESETS["omniASR_CTC_1B"]
+    w = O.init_weights(cfg, seed=0)
+    wave = bench.synthetic_windows(32, BENCH_SEED)
+    assert hashlib.sha256(wave.numpy().tobytes()).hexdigest() == str(g["bench_batch_sha256"])
+    wave = wave[:1].contiguous()
+    ns = [wave.shape[1]]
+    with torch.no_grad():
+        out = O.forward(w, O.wave_layer_norm(wave, ns), ns, cfg, return_logits=True)
+    ids = out.frame_ids[0].numpy()
+    rows = np.arange(0, 1499, ROW_STEP)
+    assert np.abs(out.hidden[0, rows].numpy() - g["hf_hidden"]).max() < 2e-4
+    agree = ids == g["hf_ids"]
+    assert agree[g["hf_margin"] > 1e-3].all() and agree.mean() > 0.995
