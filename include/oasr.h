@@ -129,6 +129,19 @@ OASR_API int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t 
                          int32_t B, int32_t L, int32_t flags, int32_t* out_ids_host, int32_t* out_frames_host,
                          int32_t* out_lens_host, int32_t* frame_ids_host, OasrStream stream);
 
+/* The same call split in two, for a host loop that keeps the GPU fed (the reference keeps up to MAX_PARALLEL_CHUNKS = 4
+ * requests in flight per recording, gemini_pipeline.py:217-219, 623-641: here the requests in flight are batches of
+ * windows).  oasr_transcribe_host_async enqueues H2D + forward + D2H and returns a ticket without waiting; at most two
+ * tickets may be outstanding per handle - each has its own device landing buffer, and the H2D copy runs on a copy
+ * stream of the engine, so the waveform of batch k + 1 crosses PCIe under the forward of batch k.  The host buffers of
+ * a ticket (PINNED memory, or the copies are not asynchronous) must stay untouched until oasr_wait(ticket) returns; the
+ * outputs are valid after it.  stream = NULL: the engine's own non-blocking stream.  Tickets complete in order. */
+OASR_API int oasr_transcribe_host_async(OasrHandle h, const float* wave_host, int64_t wave_stride,
+                               const int32_t* n_samples_host, int32_t B, int32_t L, int32_t flags, int32_t* out_ids_host,
+                               int32_t* out_frames_host, int32_t* out_lens_host, int32_t* frame_ids_host,
+                               OasrStream stream, int64_t* ticket_out);
+OASR_API int oasr_wait(OasrHandle h, int64_t ticket);
+
 /* Debug/parity: run the forward up to `stop_stage` (1 = FE, 2 = projection, 3 = pos-conv, 4+l = encoder
  * layer l, 0 = everything) and expose internal device buffers by name: "fe" bf16 [B,Tpad,512],
  * "x" fp32 [B*T,d], "wave" fp32 [B,L].  shape gets up to 4 extents (0-terminated). */

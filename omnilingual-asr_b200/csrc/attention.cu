@@ -1,8 +1,9 @@
 // a14 dispatcher: attention_v7 (persistent; three query tiles per CTA, 48-key blocks) for head_dim <= 80 (300M, 1B),
-// attention_v4 (two tiles, 96 / 80-key blocks) above (3B, 7B).  OASR_ATTN=6 selects v7's one-item-per-CTA predecessor
-// and OASR_ATTN=4 forces v4 everywhere (A/B runs).
+// attention_v4 (two tiles, 96 / 80-key blocks) above (3B, 7B).  OASR_ATTN=4 forces v4 everywhere (A/B runs; covered by
+// tests/test_gpu_kernels.py::test_attention_env_switch_v4).
 // Earlier generations (v1 two-pass reference, v2 single pass with P aliased onto S, v3 ping-pong warpgroups, v5 with
-// two warps per query row) are in the history; what each taught is in profiles/r1_notes.md.
+// two warps per query row, v6 = v7 with one work item per CTA) are in the history; what each taught is in
+// profiles/r1_notes.md.
 #include "kernels.cuh"
 
 #include <cstdlib>
@@ -15,7 +16,6 @@ int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T
     const char* e = std::getenv("OASR_ATTN");
     return e != nullptr ? std::atoi(e) : 7;
   }();
-  if (version == 6 && hd <= 80) return attention_bf16_v6(qkv, out, n_frames, B, T, H, hd, scale, stream);
   if (version != 4 && hd <= 80) return attention_bf16_v7(qkv, out, n_frames, B, T, H, hd, scale, stream);
   return attention_bf16_v4(qkv, out, n_frames, B, T, H, hd, scale, stream);
 }

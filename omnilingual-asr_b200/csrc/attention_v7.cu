@@ -564,11 +564,10 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   cudaError_t attr_err = cudaSuccess;
 #define OASR_ATT_CASE(HDV)                                                                                      \
   case HDV: {                                                                                                   \
-    static bool attr_done = false;                                                                              \
-    if (!attr_done) {                                                                                           \
+    static unsigned long long attr_mask = 0;                                                                    \
+    if (first_use_on_this_device(&attr_mask)) {                                                                 \
       attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       227 * 1024);                                                              \
-      attr_done = attr_err == cudaSuccess;                                                                      \
     }                                                                                                           \
     if (attr_err == cudaSuccess)                                                                                \
       attention_v7_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \

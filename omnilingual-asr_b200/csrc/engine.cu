@@ -152,7 +152,16 @@ struct OasrEngine {
   cudaEvent_t stage_ev[STAGE_SLOTS] = {};
   bool stage_used[STAGE_SLOTS] = {};
   int stage_next = 0;
-  float* wave_raw = nullptr;        // [B, L] H2D landing buffer of oasr_transcribe_host
+  // oasr_transcribe_host(_async): ASYNC_SLOTS landing buffers for the waveform, so that the H2D copy of batch k + 1
+  // (on h2d_stream) runs under the forward of batch k; a slot is busy from its submit to the oasr_wait of its ticket
+  static constexpr int ASYNC_SLOTS = 2;
+  float* wave_raw[ASYNC_SLOTS] = {nullptr, nullptr};   // [B, L] each
+  cudaStream_t h2d_stream = nullptr, own_stream = nullptr;
+  cudaEvent_t h2d_done[ASYNC_SLOTS] = {}, slot_done[ASYNC_SLOTS] = {};
+  bool slot_busy[ASYNC_SLOTS] = {};
+  int32_t* slot_lens_host[ASYNC_SLOTS] = {};           // empty-output case: zeroed at wait
+  int slot_B[ASYNC_SLOTS] = {};
+  int64_t tickets = 0;                                  // ticket t lives in slot t % ASYNC_SLOTS
   // optional per-stage timing (bench.py): an event at every stage boundary of the forward
   bool profiling = false;
   // CUDA graphs of the whole forward for small batches (latency path): one per (input buffer, B, L, flags), captured
@@ -286,7 +295,7 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   if (e->h_stage) cudaFreeHost(e->h_stage);
   OASR_CUDA_CHECK(cudaMallocHost((void**)&e->h_stage, (size_t)OasrEngine::STAGE_SLOTS * nB * 2 * 4));
   for (int i = 0; i < OasrEngine::STAGE_SLOTS; ++i) e->stage_used[i] = false;
-  OASR_TRY(A((void**)&e->wave_raw, (size_t)nB * nL * 4, false));
+  for (int i = 0; i < OasrEngine::ASYNC_SLOTS; ++i) OASR_TRY(A((void**)&e->wave_raw[i], (size_t)nB * nL * 4, false));
   e->ws_B = nB;
   e->ws_L = nL;
   return OASR_OK;
@@ -886,6 +895,12 @@ void oasr_destroy(OasrHandle h) {
   if (h->tp_arena) cudaFree(h->tp_arena);
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int i = 0; i < OasrEngine::ASYNC_SLOTS; ++i) {
+    if (h->h2d_done[i]) cudaEventDestroy(h->h2d_done[i]);
+    if (h->slot_done[i]) cudaEventDestroy(h->slot_done[i]);
+  }
   if (h->graph_stream) cudaStreamDestroy(h->graph_stream);
   if (h->graph_fork) cudaEventDestroy(h->graph_fork);
   if (h->graph_join) cudaEventDestroy(h->graph_join);
@@ -1285,17 +1300,81 @@ int oasr_forward_ctc(OasrHandle h, const float* wave_dev, int64_t wave_stride, c
   return OASR_OK;
 }
 
+int oasr_transcribe_host_async(OasrHandle h, const float* wave_host, int64_t wave_stride, const int32_t* n_samples_host,
+                               int32_t B, int32_t L, int32_t flags, int32_t* out_ids_host, int32_t* out_frames_host,
+                               int32_t* out_lens_host, int32_t* frame_ids_host, OasrStream stream, int64_t* ticket_out) {
+  OASR_REQUIRE(h && wave_host && out_lens_host && ticket_out, "oasr_transcribe_host_async: null argument");
+  OASR_REQUIRE(B > 0 && L > 0, "oasr_transcribe_host_async: empty batch");
+  OasrEngine* e = h;
+  const int slot = (int)(e->tickets % OasrEngine::ASYNC_SLOTS);
+  if (e->slot_busy[slot])
+    return fail(OASR_ERR_STATE, "oasr_transcribe_host_async: both slots in flight - oasr_wait the oldest ticket first");
+  if (e->h2d_stream == nullptr) {
+    OASR_CUDA_CHECK(cudaStreamCreateWithFlags(&e->h2d_stream, cudaStreamNonBlocking));
+    OASR_CUDA_CHECK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < OasrEngine::ASYNC_SLOTS; ++i) {
+      OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->h2d_done[i], cudaEventDisableTiming));
+      OASR_CUDA_CHECK(cudaEventCreateWithFlags(&e->slot_done[i], cudaEventDisableTiming));
+    }
+  }
+  // NULL = the engine's own non-blocking stream (the legacy default stream would serialise against h2d_stream's peers)
+  cudaStream_t st = stream != nullptr ? reinterpret_cast<cudaStream_t>(stream) : e->own_stream;
+  OASR_TRY(ensure_workspace(e, B, L));   // may synchronise the device and replace the landing buffers: nothing is in flight in this slot
+  const int64_t ws = wave_stride > 0 ? wave_stride : L;
+  float* dst = e->wave_raw[slot];
+  const size_t esz = (flags & OASR_FLAG_INPUT_I16) ? 2 : 4;   // PCM16 windows land as they are: half the H2D bytes
+  OASR_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)L * esz, wave_host, (size_t)ws * esz, (size_t)L * esz, B,
+                                    cudaMemcpyHostToDevice, e->h2d_stream));
+  OASR_CUDA_CHECK(cudaEventRecord(e->h2d_done[slot], e->h2d_stream));
+  OASR_CUDA_CHECK(cudaStreamWaitEvent(st, e->h2d_done[slot], 0));
+  OASR_TRY(forward_impl(e, dst, L, n_samples_host, B, L, flags, 0, nullptr, st));
+  const size_t n = (size_t)B * e->last_T * 4;
+  e->slot_lens_host[slot] = nullptr;
+  if (e->last_T > 0) {
+    if (out_ids_host) OASR_CUDA_CHECK(cudaMemcpyAsync(out_ids_host, e->out_ids, n, cudaMemcpyDeviceToHost, st));
+    if (out_frames_host) OASR_CUDA_CHECK(cudaMemcpyAsync(out_frames_host, e->out_frames, n, cudaMemcpyDeviceToHost, st));
+    if (frame_ids_host) OASR_CUDA_CHECK(cudaMemcpyAsync(frame_ids_host, e->frame_ids, n, cudaMemcpyDeviceToHost, st));
+    OASR_CUDA_CHECK(cudaMemcpyAsync(out_lens_host, e->out_lens, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+  } else {
+    e->slot_lens_host[slot] = out_lens_host;   // windows too short for a single frame: no device work, lengths are zero
+  }
+  OASR_CUDA_CHECK(cudaEventRecord(e->slot_done[slot], st));
+  e->slot_busy[slot] = true;
+  e->slot_B[slot] = B;
+  *ticket_out = e->tickets++;
+  return OASR_OK;
+}
+
+int oasr_wait(OasrHandle h, int64_t ticket) {
+  OASR_REQUIRE(h, "oasr_wait: null handle");
+  OasrEngine* e = h;
+  OASR_REQUIRE(ticket >= 0 && ticket < e->tickets && ticket + OasrEngine::ASYNC_SLOTS >= e->tickets,
+               "oasr_wait: unknown or already recycled ticket");
+  const int slot = (int)(ticket % OasrEngine::ASYNC_SLOTS);
+  if (!e->slot_busy[slot]) return OASR_OK;   // waited already
+  const cudaError_t ce = cudaEventSynchronize(e->slot_done[slot]);
+  e->slot_busy[slot] = false;                // only now may a submit reuse the slot's landing buffer
+  if (ce != cudaSuccess) return fail(OASR_ERR_CUDA, std::string("oasr_wait: ") + cudaGetErrorString(ce));
+  if (e->slot_lens_host[slot] != nullptr) memset(e->slot_lens_host[slot], 0, (size_t)e->slot_B[slot] * 4);
+  return OASR_OK;
+}
+
 int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stride, const int32_t* n_samples_host,
                          int32_t B, int32_t L, int32_t flags, int32_t* out_ids_host, int32_t* out_frames_host,
                          int32_t* out_lens_host, int32_t* frame_ids_host, OasrStream stream) {
   OASR_REQUIRE(h && wave_host && out_lens_host, "oasr_transcribe_host: null argument");
   OASR_REQUIRE(B > 0 && L > 0, "oasr_transcribe_host: empty batch");
+  // the synchronous form keeps its stream contract: NULL is the (legacy) default stream, as in round 1
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (int i = 0; i < OasrEngine::ASYNC_SLOTS; ++i)   // drain: the synchronous call may not overtake pending tickets
+    if (h->slot_busy[(h->tickets + i) % OasrEngine::ASYNC_SLOTS]) {
+      const int slot = (int)((h->tickets + i) % OasrEngine::ASYNC_SLOTS);
+      OASR_CUDA_CHECK(cudaEventSynchronize(h->slot_done[slot]));
+    }
   OASR_TRY(ensure_workspace(h, B, L));
   const int64_t ws = wave_stride > 0 ? wave_stride : L;
-  float* dst = h->wave_raw;
-  void* tmp = nullptr;
-  const size_t esz = (flags & OASR_FLAG_INPUT_I16) ? 2 : 4;   // PCM16 windows land as they are: half the H2D bytes
+  float* dst = h->wave_raw[0];
+  const size_t esz = (flags & OASR_FLAG_INPUT_I16) ? 2 : 4;
   cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)L * esz, wave_host, (size_t)ws * esz, (size_t)L * esz, B,
                                      cudaMemcpyHostToDevice, st);
   int rc = OASR_OK;
@@ -1313,7 +1392,6 @@ int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stri
   }
   ce = cudaStreamSynchronize(st);
   if (rc == OASR_OK && ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(ce));
-  if (tmp) cudaFree(tmp);
   return rc;
 }
 

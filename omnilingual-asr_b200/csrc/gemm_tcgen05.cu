@@ -54,17 +54,17 @@ constexpr bool epi_has_resid(int epi) { return epi == EPI_F32_RESID || epi == EP
 // 256 TMEM columns and can be double-buffered: the next tile's MMAs run under the three-pass LayerNorm epilogue, which
 // with a 512-column accumulator had the tensor pipe idle 43 % of the time.  The row statistics are completed through
 // distributed shared memory (each warp writes its partial into both CTAs, one cluster-scope mbarrier per pass).
-constexpr bool epi_nsplit(int bn, int epi) { return epi == EPI_LN_GELU_BF16 && bn == 256; }
+constexpr bool epi_nsplit(int bn, int epi) { return epi == EPI_LN_GELU_BF16; }
 
 template <int BN, int CG, int EPI>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int ACC_STAGES = BN <= 256 ? 2 : 1;
+  static_assert(BN <= 256, "a tile is one tcgen05.mma wide; the accumulator is double-buffered in TMEM");
+  static constexpr int ACC_STAGES = 2;
   static constexpr int TMEM_COLS_RAW = BN * ACC_STAGES;
   static constexpr int TMEM_COLS = TMEM_COLS_RAW <= 32 ? 32 : TMEM_COLS_RAW <= 64 ? 64 : TMEM_COLS_RAW <= 128 ? 128 : TMEM_COLS_RAW <= 256 ? 256 : 512;
-  static constexpr int UMMA_N = BN > 256 ? 256 : BN;
   static constexpr int BAR_BYTES = 5120;  // barriers (<256 B), LN scratch red1 (2 KB at +256), epilogue barriers (+2304), red2 (2 KB at +2560)
   // epilogue staging: per-warp [32][20] word transpose buffers, or (residual epilogues) per warp two 64B-swizzled
   // [32 rows][RES_CW fp32] tiles that TMA fills with the residual and stores back as the output (16 columns: 32 KB
@@ -166,7 +166,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // This single thread must issue one stage per ~512 MMA cycles: the loop carries its coordinates incrementally
       // (no division, nothing recomputed per k-block) - a 113-instruction body with two integer divisions measured
       // ~675 cycles per iteration and starved the tensor pipe (profiles/r1_notes.md).
-      const int n_boxes = (BN > 256 && p.N > 256) ? 2 : 1;   // W boxes per stage
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         const int w_row = t.n_tile * BN + (CG == 2 ? cta_rank * p.b_box_rows : 0);
@@ -181,12 +180,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (leader) mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
             tma_load_5d_cg2(sA, &tmA, bar, c0, par, pos, t.b, t.g);
             tma_load_3d_cg2(sB, &tmB, bar, wk, w_row, t.g);
-            if (n_boxes == 2) tma_load_3d_cg2(sB + 128 * (BK * 2), &tmB, bar, wk, w_row + 256, t.g);
           } else {
             mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes);
             tma_load_5d(sA, &tmA, &full[s], c0, par, pos, t.b, t.g);
             tma_load_3d(sB, &tmB, &full[s], wk, w_row, t.g);
-            if (n_boxes == 2) tma_load_3d(sB + 256 * (BK * 2), &tmB, &full[s], wk, w_row + 256, t.g);
           }
           wk += BK;
           c0 += BK;
@@ -213,7 +210,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = make_idesc_bf16(BM * CG, p.umma_n, 0, 0);
       constexpr uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (uint32_t(SWZ_128B) << 29);  // SBO, v1, layout
       const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);                      // LBO field = 1
-      const bool two_chunks = BN > 256 && p.N > 256;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -236,13 +232,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if constexpr (CG == 2) umma_ss_cg2(d_tmem, adesc, bdesc, idesc, acc);
               else umma_ss(d_tmem, adesc, bdesc, idesc, acc);
             }
-            if constexpr (BN > 256) {   // second 256-column MMA of a 512-wide tile
-              const uint64_t bdesc2 = bdesc + ((256 / CG) * (BK * 2) >> 4);
-              if (issuer && two_chunks) {
-                if constexpr (CG == 2) umma_ss_cg2(d_tmem + 256, adesc, bdesc2, idesc, acc);
-                else umma_ss(d_tmem + 256, adesc, bdesc2, idesc, acc);
-              }
-            }
           }
           // frees the smem stage (in both CTAs of a pair) when these MMAs retire
           if (issuer) {
@@ -257,12 +246,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if constexpr (CG == 2) umma_commit_cg2(&tfull[as], 3); else umma_commit(&tfull[as]);
         }
         __syncwarp();
-        if (C::ACC_STAGES == 2) {
-          as ^= 1;
-          if (as == 0) aph ^= 1;
-        } else {
-          aph ^= 1;
-        }
+        as ^= 1;
+        if (as == 0) aph ^= 1;
       }
     }
   } else if (warp >= 4) {
@@ -302,7 +287,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t peer_red1 = NSPLIT ? mapa_u32(smem_u32(red1), cluster_rank ^ 1) : 0u;
     const uint32_t peer_red2 = NSPLIT ? mapa_u32(smem_u32(red2), cluster_rank ^ 1) : 0u;
     const uint32_t peer_ln_bar = NSPLIT ? mapa_u32(smem_u32(&ln_bar[q * 2]), cluster_rank ^ 1) : 0u;
-    constexpr int LN_N = NSPLIT ? 2 * BN : BN;   // channels of a row
+    constexpr int LN_N = 2 * BN;   // channels of a row (LayerNorm epilogue: split over the two CTAs of the cluster)
     auto ln_exchange = [&](float* red, uint32_t peer_red, int pass, float part, int row) -> float {
       const int slot = (cluster_rank * 2 + half) * 128 + row;
       red[slot] = part;
@@ -437,14 +422,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }, false);
         float sa, sb;
         f2_unpack(f2_add(acc0, acc1), sa, sb);
-        float mean;
-        if constexpr (NSPLIT) {
-          mean = ln_exchange(red1, peer_red1, 0, sa + sb + ln_bias_sum, row_in_tile) * (1.0f / LN_N);
-        } else {
-          red1[half * 128 + row_in_tile] = sa + sb + ln_bias_sum;
-          named_bar_sync(1 + q, 64);
-          mean = (red1[row_in_tile] + red1[128 + row_in_tile]) * (1.0f / BN);
-        }
+        const float mean = ln_exchange(red1, peer_red1, 0, sa + sb + ln_bias_sum, row_in_tile) * (1.0f / LN_N);
         const f32x2 nmean2 = f2_splat(-mean);
         acc0 = 0ull;
         acc1 = 0ull;
@@ -459,15 +437,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }, false);
         f2_unpack(f2_add(acc0, acc1), sa, sb);
-        float var;
-        if constexpr (NSPLIT) {
-          var = ln_exchange(red2, peer_red2, 1, sa + sb, row_in_tile) * (1.0f / LN_N);
-          ln_ph ^= 1;
-        } else {
-          red2[half * 128 + row_in_tile] = sa + sb;
-          named_bar_sync(1 + q, 64);
-          var = (red2[row_in_tile] + red2[128 + row_in_tile]) * (1.0f / BN);
-        }
+        const float var = ln_exchange(red2, peer_red2, 1, sa + sb, row_in_tile) * (1.0f / LN_N);
+        ln_ph ^= 1;
         const f32x2 rstd2 = f2_splat(rsqrtf(var + 1e-5f));
         const ulonglong2* wgamma2 = reinterpret_cast<const ulonglong2*>(wbias + BN);
         const ulonglong2* wbeta2 = reinterpret_cast<const ulonglong2*>(wbias + 2 * BN);
@@ -620,12 +591,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
 
       __syncwarp();   // every lane is done with this tile's bias slice
-      if (C::ACC_STAGES == 2) {
-        as ^= 1;
-        if (as == 0) aph ^= 1;
-      } else {
-        aph ^= 1;
-      }
+      as ^= 1;
+      if (as == 0) aph ^= 1;
     }
     if constexpr (HAS_RESID) {
       if (lane == 0) bulk_wait_group_read<0>();   // shared memory must outlive the last TMA store's read
@@ -697,9 +664,9 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.k_blocks = p.kb_per_tap * a.taps;
   p.P = a.P;
   const int n_cap = a.N < BN ? ((a.N + 15) / 16) * 16 : BN;   // columns one tile really computes
-  p.umma_n = n_cap > 256 ? 256 : n_cap;
+  p.umma_n = n_cap;
   p.b_box_rows = p.umma_n / CG;   // W rows one CTA fetches per MMA-N chunk
-  p.stage_tx_bytes = (uint32_t)CG * (C::A_BYTES + (uint32_t)((n_cap + p.umma_n - 1) / p.umma_n) * p.b_box_rows * BK * 2);
+  p.stage_tx_bytes = (uint32_t)CG * (C::A_BYTES + (uint32_t)p.b_box_rows * BK * 2);
   p.ldo = a.ldo;
   p.out_batch_rows = a.out_batch_rows > 0 ? a.out_batch_rows : a.rows_per_batch;
   p.out = a.out;
@@ -758,12 +725,10 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
     }
   }
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_this_device(&attr_mask))
     OASR_CUDA_CHECK(cudaFuncSetAttribute(gemm_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::SMEM_BYTES));
-    attr_done = true;
-  }
   constexpr bool NSPLIT = epi_nsplit(BN, EPI);
   const int units = device_sm_count() / CG;   // CTAs or CTA pairs that can be resident
   int grid_units = p.total_tiles < units ? p.total_tiles : units;
@@ -841,14 +806,7 @@ int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
     case EPI_LN_GELU_BF16:
       OASR_REQUIRE(a.N == 512 && a.groups == 1 && a.bias && a.ln_gamma && a.ln_beta,
                    "gemm: LN epilogue needs N == 512 and bias/gamma/beta");
-      {
-        static const bool split = [] {
-          const char* e = std::getenv("OASR_FE_NSPLIT");   // 0: one 512-column accumulator per CTA pair (A/B runs)
-          return e == nullptr || std::atoi(e) != 0;
-        }();
-        if (split) return launch_cg<256, EPI_LN_GELU_BF16, 1>(a, stream);
-      }
-      return launch<512, EPI_LN_GELU_BF16>(a, stream);
+      return launch_cg<256, EPI_LN_GELU_BF16, 1>(a, stream);
     default: return fail(OASR_ERR_INVALID, "gemm: unknown epilogue");
   }
 }

@@ -25,6 +25,13 @@ int device_sm_count() {
   return cached[dev];
 }
 
+bool first_use_on_this_device(unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  const unsigned long long bit = 1ull << dev;
+  return (__atomic_fetch_or(mask, bit, __ATOMIC_ACQ_REL) & bit) == 0;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

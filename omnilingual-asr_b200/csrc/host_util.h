@@ -35,6 +35,10 @@ int fail(int code, const std::string& msg);
 
 int device_sm_count();
 
+// cudaFuncSetAttribute is per DEVICE: a process that drives several GPUs (one engine per GPU, engine_pool.py) has to
+// set a kernel's dynamic shared-memory limit on each of them.  `mask` = one static bit set per kernel instantiation.
+bool first_use_on_this_device(unsigned long long* mask);
+
 // bf16 tensor map, rank 2..5.  dims[0] is the contiguous dimension; strides_bytes[i] is the byte
 // stride of dims[i+1] (rank-1 entries, each a multiple of 16).  OOB elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

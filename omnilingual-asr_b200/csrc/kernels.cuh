@@ -55,8 +55,6 @@ int attention_bf16(const void* qkv, void* out, const int* n_frames, int B, int T
                    cudaStream_t stream);
 int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream);
-int attention_bf16_v6(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
-                      cudaStream_t stream);
 int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, int T, int H, int hd, float scale,
                       cudaStream_t stream);
 

@@ -48,6 +48,9 @@ _PROTOTYPES = {
     "oasr_feature_length": (_i32, [C.POINTER(OasrConfig), _i64]),
     "oasr_forward_ctc": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "oasr_transcribe_host": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "oasr_transcribe_host_async": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
+                                             C.POINTER(_i64)]),
+    "oasr_wait": (C.c_int, [_vp, _i64]),
     "oasr_debug_forward": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
     "oasr_debug_buffer": (C.c_int, [_vp, C.c_char_p, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
     "oasr_debug_copy": (C.c_int, [_vp, C.c_char_p, _vp, _i64]),

@@ -211,6 +211,41 @@ class CtcEngine:
             n_frames=[self.cfg.feature_length(int(v)) for v in n_samples],
             frame_ids=fids[:, :T] if fids is not None else None)
 
+    # ------------------------------------------------------------------ asynchronous host loop (engine_pool.py)
+    def submit_host(self, wave: np.ndarray, n_samples: Sequence[int], out_ids: np.ndarray, out_frames: np.ndarray,
+                    out_lens: np.ndarray, *, stream=0) -> int:
+        """oasr_transcribe_host_async: enqueue H2D + forward + D2H of a [B, L] batch held in PINNED host memory and
+        return a ticket at once (at most two outstanding per engine).  `wave` (float32 or PCM16) and the three output
+        arrays (int32, pinned, [B, >= T] / [B]) belong to the engine until `wait(ticket)` returns.  stream = 0: the
+        engine's own non-blocking stream."""
+        if wave.ndim != 2 or wave.dtype not in (np.float32, np.int16) or wave.strides[1] != wave.itemsize:
+            raise ValueError("wave must be a [B, L] float32 or int16 array with unit inner stride")
+        B, L = wave.shape
+        if len(n_samples) != B:
+            raise ValueError("n_samples must have one entry per window")
+        T = max(self.feature_length(L), 1)
+        for a, shape in ((out_ids, (B, T)), (out_frames, (B, T))):
+            if a.dtype != np.int32 or a.ndim != 2 or a.shape[0] < B or a.shape[1] != T or not a.flags.c_contiguous:
+                raise ValueError(f"output arrays must be C-contiguous int32 [>= {B}, {T}]")
+        if out_lens.dtype != np.int32 or out_lens.size < B:
+            raise ValueError("out_lens must be int32 [>= B]")
+        flags = N.FLAG_INPUT_I16 if wave.dtype == np.int16 else 0
+        ns = (C.c_int32 * B)(*[int(v) for v in n_samples])
+        ticket = C.c_int64(-1)
+        with self._lock, torch.cuda.device(self.device):
+            N.check(self._lib.oasr_transcribe_host_async(
+                self._handle, N.ptr(wave), wave.strides[0] // wave.itemsize, C.cast(ns, C.c_void_p), B, L, flags,
+                N.ptr(out_ids), N.ptr(out_frames), N.ptr(out_lens), C.c_void_p(0),
+                C.c_void_p(int(getattr(stream, "cuda_stream", stream) or 0)), C.byref(ticket)),
+                "oasr_transcribe_host_async")
+        return int(ticket.value)
+
+    def wait(self, ticket: int) -> None:
+        """oasr_wait: block (GIL released) until the ticket's outputs are in host memory.  Not under the engine lock:
+        it only waits for an event, so another thread may submit meanwhile."""
+        with torch.cuda.device(self.device):
+            N.check(self._lib.oasr_wait(self._handle, int(ticket)), "oasr_wait")
+
     # ------------------------------------------------------------------ device-side audio front end
     def resample_to_model_rate(self, samples: np.ndarray | torch.Tensor, sample_rate: int) -> torch.Tensor:
         """[n] or [n, channels] fp32 / PCM16 samples at `sample_rate` -> mono fp32 DEVICE tensor at 16 kHz

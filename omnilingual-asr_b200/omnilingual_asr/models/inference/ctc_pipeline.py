@@ -9,12 +9,14 @@ Mirrors src/omnilingual_asr/models/inference/gemini_pipeline.py of the reference
   * progress steps ("uploading",0) ("transcribing",1) ("processing",2) ("done",3)   <- :486-487
   * errors: ValueError for configuration, RuntimeError("Failed to transcribe after N attempts: ...")
     after retries (:329-334, :739-741)
-The per-chunk HTTPS call (:512-530) is replaced by CtcEngine.transcribe_host -> liboasr (sm_100a).
+The per-chunk HTTPS call (:512-530) is replaced by liboasr (sm_100a): windows go through an EnginePool
+(engine_pool.py) - one engine and one worker thread per GPU behind a queue shared by all callers, two batches in
+flight per engine (oasr_transcribe_host_async / oasr_wait).  One pipeline object in one process drives every GPU it
+was given (`devices="all"`), which is how the reference's web app holds it (workflows/wav2elan_web/app.py:38-54).
 Unlike the reference a failed window is never dropped silently (:635-641): a CUDA failure raises.
 """
 from __future__ import annotations
 
-import threading
 import time
 from dataclasses import dataclass, field
 from pathlib import Path
@@ -26,6 +28,7 @@ from omnilingual_asr.models.config import SAMPLE_RATE, CtcModelConfig, get_model
 from omnilingual_asr.models.inference.audio import (get_audio_duration, load_audio_16k, ownership_bounds, read_wav,
                                                     shard_range, split_into_overlapping_windows, split_into_windows,
                                                     to_mono_16k)
+from omnilingual_asr.models.inference.engine_pool import EnginePool, WindowTokens
 from omnilingual_asr.models.inference.tokenizer import CtcVocabulary
 
 # Window constants (the reference's CHUNK_DURATION_SECONDS / MIN_DURATION_FOR_CHUNKING / MAX_PARALLEL_CHUNKS,
@@ -68,24 +71,13 @@ class CTCTranscriptionResult:
     detected_languages: Optional[List[dict]] = None
 
 
-@dataclass
-class WindowTokens:
-    """Decoded tokens of one window, before text shaping (what travels between ranks)."""
-    index: int
-    start_sample: int
-    n_samples: int
-    n_frames: int
-    token_ids: np.ndarray
-    token_frames: np.ndarray
-
-
 AudioInput = Any  # path | np.ndarray | torch.Tensor | {"waveform": ..., "sample_rate": ...}
 
 
 def _resolve_audio(audio: AudioInput, sample_rate: Optional[int], engine: Any = None):
-    """Anything the boundary accepts -> mono samples at 16 kHz: a host array (float32, or PCM16 left as it is), or -
-    when the audio needs a channel mix or a rate change and the engine has the device-side front end - a float32
-    DEVICE tensor produced by oasr_resample."""
+    """Anything the boundary accepts -> mono samples at 16 kHz as a host array (float32, or PCM16 left as it is); audio
+    that needs a channel mix or a rate change goes through the device-side front end (oasr_resample) when the engine
+    has one."""
     if isinstance(audio, (str, Path)):
         p = Path(audio)
         if engine is not None and hasattr(engine, "resample_to_model_rate") and p.exists() \
@@ -107,41 +99,12 @@ def _resolve_audio(audio: AudioInput, sample_rate: Optional[int], engine: Any = 
         x = x[:, 0]
     needs_front_end = sr != SAMPLE_RATE or x.ndim == 2
     if needs_front_end and engine is not None and hasattr(engine, "resample_to_model_rate"):
-        return engine.resample_to_model_rate(x, sr)
+        # channel mix + polyphase resampling on the device (oasr_resample); the 16 kHz mono result comes back to the host
+        # because its windows may be served by any GPU of the pool
+        return engine.resample_to_model_rate(x, sr).cpu().numpy()
     if x.dtype == np.int16:
         x = x.astype(np.float32) / 32768.0
     return to_mono_16k(x, sr)
-
-
-class _pinned:
-    """Page-locks a large host array for the duration of a call (cudaHostRegister); a no-op for small arrays, fake
-    engines or when registration is refused."""
-
-    MIN_BYTES = 64 << 20
-
-    def __init__(self, arr: np.ndarray, engine: Any) -> None:
-        self.ptr = None
-        if not isinstance(arr, np.ndarray) or getattr(engine, "device", None) is None or arr.nbytes < self.MIN_BYTES \
-                or not arr.flags.c_contiguous:
-            return
-        try:
-            import torch
-            self.rt = torch.cuda.cudart()
-            if int(self.rt.cudaHostRegister(arr.ctypes.data, arr.nbytes, 0)) == 0:
-                self.ptr = arr.ctypes.data
-        except Exception:
-            self.ptr = None
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *exc):
-        if self.ptr is not None:
-            try:
-                self.rt.cudaHostUnregister(self.ptr)
-            except Exception:
-                pass
-        return False
 
 
 def build_segments(win: WindowTokens, vocab: CtcVocabulary, *, word_timestamps: bool,
@@ -248,7 +211,8 @@ class CTCASRPipeline:
 
     def __init__(self, model_card: str | CtcModelConfig = "omniASR_CTC_1B", *,
                  weights: Any = None, vocabulary: Optional[CtcVocabulary | Sequence[str]] = None,
-                 device: Any = None, engine: Any = None, window_seconds: float = CHUNK_DURATION_SECONDS,
+                 device: Any = None, devices: Any = None, engine: Any = None, engines: Optional[Sequence[Any]] = None,
+                 window_seconds: float = CHUNK_DURATION_SECONDS,
                  batch_windows: int = MAX_PARALLEL_CHUNKS, split_gap_sec: Optional[float] = None,
                  overlap_seconds: float = 0.0, seed: int = 0, distributed: bool = True) -> None:
         self.cfg = get_model_config(model_card)
@@ -273,18 +237,57 @@ class CTCASRPipeline:
         if len(vocabulary) != self.cfg.vocab:
             raise ValueError(f"vocabulary has {len(vocabulary)} entries, model expects {self.cfg.vocab}")
         self.vocab = vocabulary
-        self._lock = threading.Lock()   # one GPU submission at a time (app.py shares one pipeline over 4 threads)
-        if engine is not None:
-            self.engine = engine
+        self._owns_engines = False
+        if engine is not None or engines:
+            self.engines = list(engines) if engines else [engine]
         else:
             if weights is None:
                 raise ValueError(
                     "no weights given: pass weights=<state dict | path to a torch checkpoint> or weights='random' "
                     "(deterministic random init; there are no omniASR checkpoints offline)")
-            from omnilingual_asr.models.inference.ctc_engine import CtcEngine  # needs liboasr.so + CUDA
-            from omnilingual_asr.models.weights import resolve_weights
-            self.engine = CtcEngine(self.cfg, device=device)
-            self.engine.load_state_dict(resolve_weights(self.cfg, weights, seed, self.engine.device))
+            self.engines = self._build_engines(device, devices, weights, seed)
+            self._owns_engines = True
+        self.engine = self.engines[0]     # the audio front end (oasr_resample) and single-engine callers use this one
+        # concurrent transcribe calls (app.py shares one pipeline over 4 threads) meet in the pool's queue: their
+        # windows are packed into common batches instead of waiting for each other on a lock
+        self.pool = EnginePool(self.engines, self.batch_windows)
+
+    def _build_engines(self, device: Any, devices: Any, weights: Any, seed: int) -> List[Any]:
+        """One CtcEngine per GPU: `devices` = "all" | a list of devices / indices | None (= `device`, or the current one).
+        Replicas are loaded in parallel, each on its own device."""
+        import torch
+        from concurrent.futures import ThreadPoolExecutor
+        from omnilingual_asr.models.inference.ctc_engine import CtcEngine  # needs liboasr.so + CUDA
+        from omnilingual_asr.models.weights import resolve_weights
+        if devices is None:
+            devs = [device]
+        elif isinstance(devices, str):
+            if devices != "all":
+                raise ValueError('devices must be "all", a list of devices or None')
+            if not torch.cuda.is_available():
+                raise RuntimeError("omniASR CTC engine needs a CUDA device (B200, sm_100a); none is visible")
+            devs = [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+        else:
+            devs = [torch.device("cuda", d) if isinstance(d, int) else torch.device(d) for d in devices]
+            if not devs:
+                raise ValueError("devices is empty")
+
+        def make(dev):
+            eng = CtcEngine(self.cfg, device=dev)
+            eng.load_state_dict(resolve_weights(self.cfg, weights, seed, eng.device))
+            return eng
+
+        if len(devs) == 1:
+            return [make(devs[0])]
+        with ThreadPoolExecutor(max_workers=len(devs)) as ex:
+            return list(ex.map(make, devs))
+
+    def close(self) -> None:
+        """Stop the worker threads; engines the pipeline created itself are destroyed."""
+        self.pool.close()
+        if self._owns_engines:
+            for e in self.engines:
+                e.close()
 
     # ------------------------------------------------------------------ device step
     def _rank_world(self) -> Tuple[int, int]:
@@ -310,46 +313,8 @@ class CTCASRPipeline:
         return rank, world
 
     def _run_windows(self, wave: np.ndarray, windows: List[Tuple[int, int]], lo: int, hi: int) -> List[WindowTokens]:
-        """Windows [lo, hi) through the engine in batches; host buffers in, token ids out."""
-        out: List[WindowTokens] = []
-        on_device = not isinstance(wave, np.ndarray)      # torch tensor from the device-side front end
-        for b0 in range(lo, hi, self.batch_windows):
-            idx = list(range(b0, min(hi, b0 + self.batch_windows)))
-            L = max(windows[i][1] for i in idx)
-            s0 = windows[idx[0]][0]
-            if on_device:
-                contiguous = all(windows[i] == (s0 + r * L, L) for r, i in enumerate(idx))
-                if contiguous:
-                    batch = wave[s0:s0 + len(idx) * L].view(len(idx), L)
-                else:
-                    batch = wave.new_zeros((len(idx), L))
-                    for r, i in enumerate(idx):
-                        s, n = windows[i]
-                        batch[r, :n] = wave[s:s + n]
-                ns = [windows[i][1] for i in idx]
-                with self._lock:
-                    res = self.engine.forward(batch, ns, return_frame_ids=False)
-                for r, i in enumerate(idx):
-                    out.append(WindowTokens(i, windows[i][0], windows[i][1], int(res.n_frames[r]),
-                                            np.asarray(res.token_ids[r], dtype=np.int32),
-                                            np.asarray(res.token_frames[r], dtype=np.int32)))
-                continue
-            if all(windows[i] == (s0 + r * L, L) for r, i in enumerate(idx)) and wave.flags.c_contiguous:
-                # full, back-to-back windows: the batch is a [B, L] view of the recording itself (no host copy)
-                batch = wave[s0:s0 + len(idx) * L].reshape(len(idx), L)
-            else:
-                batch = np.zeros((len(idx), L), dtype=wave.dtype if wave.dtype == np.int16 else np.float32)
-                for r, i in enumerate(idx):
-                    s, n = windows[i]
-                    batch[r, :n] = wave[s:s + n]
-            ns = [windows[i][1] for i in idx]
-            with self._lock:
-                res = self.engine.transcribe_host(batch, ns)
-            for r, i in enumerate(idx):
-                out.append(WindowTokens(i, windows[i][0], windows[i][1], int(res.n_frames[r]),
-                                        np.asarray(res.token_ids[r], dtype=np.int32),
-                                        np.asarray(res.token_frames[r], dtype=np.int32)))
-        return out
+        """Windows [lo, hi) through the engine pool; host samples in, token ids out."""
+        return self.pool.run_windows(wave, windows, lo, hi)
 
     def _transcribe_wave(self, wave: np.ndarray, *, progress_callback, language, word_timestamps,
                          chunked: bool) -> CTCTranscriptionResult:
@@ -370,8 +335,7 @@ class CTCASRPipeline:
         failure: Optional[BaseException] = None
         mine: List[WindowTokens] = []
         try:
-            with _pinned(wave, self.engine):      # long recordings: page-lock once so that every window copy is a DMA
-                mine = self._run_windows(wave, windows, lo, hi)
+            mine = self._run_windows(wave, windows, lo, hi)
         except Exception as e:  # noqa: BLE001 - a failing rank must still take part in the gather below
             if world <= 1:
                 raise

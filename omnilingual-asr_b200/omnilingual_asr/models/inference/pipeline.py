@@ -9,8 +9,6 @@ from __future__ import annotations
 
 from typing import Any, List, Optional, Sequence
 
-import numpy as np
-
 from omnilingual_asr.models.config import SAMPLE_RATE
 from omnilingual_asr.models.inference.ctc_pipeline import (MAX_ALLOWED_AUDIO_SEC, CTCASRPipeline, _resolve_audio)
 
@@ -32,16 +30,12 @@ class ASRInferencePipeline:
         for w in waves:
             if len(w) > MAX_ALLOWED_AUDIO_SEC * SAMPLE_RATE:
                 raise ValueError(f"audio longer than {MAX_ALLOWED_AUDIO_SEC} s is not supported by this entry point")
+        # clips sorted by length so that a batch pads little; the pool packs them (batch_size bounds a batch)
+        order = sorted(range(len(waves)), key=lambda i: len(waves[i]))
         texts: List[str] = [""] * len(waves)
-        order = sorted(range(len(waves)), key=lambda i: len(waves[i]))   # bucket by length, pad with zeros
         for b0 in range(0, len(order), batch_size):
             idx = order[b0:b0 + batch_size]
-            L = max(max(len(waves[i]) for i in idx), 1)
-            batch = np.zeros((len(idx), L), dtype=np.float32)
-            for r, i in enumerate(idx):
-                batch[r, :len(waves[i])] = waves[i]
-            with self._ctc._lock:
-                res = self._ctc.engine.transcribe_host(batch, [len(waves[i]) for i in idx])
-            for r, i in enumerate(idx):
-                texts[i] = self._ctc.vocab.decode(res.token_ids[r])
+            toks = self._ctc.pool.run_clips([waves[i] for i in idx])
+            for i, t in zip(idx, toks):
+                texts[i] = self._ctc.vocab.decode(t.token_ids)
         return texts

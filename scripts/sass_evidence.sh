@@ -8,7 +8,7 @@ echo "# SASS evidence (cuobjdump -sass of the sm_100a objects behind liboasr.so)
 echo
 echo "| object | kernels | UTCHMMA | UTCBAR | LDTM | STTM | UTMALDG | UTMASTG | UTMAPF | SYNCS | HMMA | FFMA2 | MUFU.EX2 |"
 echo "|---|---|---|---|---|---|---|---|---|---|---|---|---|"
-for f in gemm_tcgen05 attention_v4 attention_v6 attention_v7 norm_conv0 decode tp_fused resample; do
+for f in gemm_tcgen05 attention_v4 attention_v7 norm_conv0 decode tp_fused resample; do
   s=$(cuobjdump -sass build/$f.o 2>/dev/null)
   c() { grep -c "$1" <<<"$s"; }
   echo "| $f | $(c 'Function :') | $(c UTCHMMA) | $(c UTCBAR) | $(c LDTM) | $(c STTM) | $(c UTMALDG) | $(c UTMASTG) | $(c UTMAPF) | $(c SYNCS) | $(c ' HMMA') | $(c FFMA2) | $(c 'MUFU.EX2') |"

@@ -35,6 +35,20 @@ class OracleEngine:
         return CtcBatchResult(ids, frames, out.n_frames, out.frame_ids.numpy() if return_frame_ids else None)
 
 
+    # the asynchronous pair the engine pool drives (CtcEngine.submit_host / wait): computed at submit time here
+    def submit_host(self, wave, n_samples, out_ids, out_frames, out_lens, *, stream=0):
+        res = self.transcribe_host(wave, n_samples)
+        for b, (i, f) in enumerate(zip(res.token_ids, res.token_frames)):
+            out_lens[b] = len(i)
+            out_ids[b, :len(i)] = i
+            out_frames[b, :len(i)] = f
+        self.tickets = getattr(self, "tickets", 0) + 1
+        return self.tickets - 1
+
+    def wait(self, ticket):
+        return None
+
+
 class FlakyEngine(OracleEngine):
     """Fails the first `fail` calls with a RuntimeError (retry path)."""
     def __init__(self, fail, **kw):

@@ -186,7 +186,7 @@ def test_config1_300m_gettysburg(device):
     assert agree >= 0.95 and a_hf >= 0.95
     n, ok = tab[NEAR_TIE]
     assert ok == n                                               # 100 % on the fp32-accum check at the stated margin
-    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0]
+    assert tab[1e-2][0] - tab[1e-2][1] <= 2 and tab[1e-3][1] >= 0.99 * tab[1e-3][0]   # measured floors
     eng.close()
 
 
@@ -220,7 +220,7 @@ def test_config2_1b_full_window_against_committed_oracle(device):
     tab = margin_table(ids, gold["ids_emu"], gold["margin_emu"])
     print("1B window: vs bf16-operand oracle " + fmt_table(tab))
     assert a_emu_clear == 1.0 and a_f32 >= 0.95
-    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0]
+    assert tab[1e-2][0] - tab[1e-2][1] <= 2 and tab[1e-3][1] >= 0.99 * tab[1e-3][0]   # measured floors
     assert e_emu < 1e-2 and e_f32 < 1e-2
     eng.close()
 
@@ -244,7 +244,7 @@ def _check_fullsize_window(tag, ids, hidden_rows, g, b):
     print(msg)
     n, ok = tab[NEAR_TIE]
     assert ok == n, msg                              # 100 % on the fp32-accum check at the stated margin
-    assert tab[1e-2][1] >= 0.99 * tab[1e-2][0] and tab[1e-3][1] >= 0.98 * tab[1e-3][0], msg
+    assert tab[1e-2][0] - tab[1e-2][1] <= 2 and tab[1e-3][1] >= 0.99 * tab[1e-3][0], msg   # measured floors
     assert a_f32 >= 0.95 and e_emu < 1e-2 and e_f32 < 1e-2, msg
 
 
@@ -432,20 +432,24 @@ def test_config1_file_through_the_device_front_end(device):
 
 def test_one_pipeline_shared_by_four_threads(device):
     """The web app shares ONE pipeline object between up to four worker threads (workflows/wav2elan_web/app.py:38-54,
-    384-389): concurrent transcribe calls must serialise on the handle and return what a lone call returns."""
+    384-389): concurrent transcribe calls meet in the engine pool's queue, their windows leave in COMMON batches
+    (cross-caller batching), and every caller gets what a lone call returns."""
     import threading
     from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
     ocfg, w, eng = make_engine("tiny", device)
-    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=3, distributed=False)
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=16, distributed=False)
     rng = np.random.default_rng(11)
     clips = [(rng.standard_normal(16000 * 4 + 123 * i) * 0.2).astype(np.float32) for i in range(4)]
     want = [[(s.start, s.end, s.text) for s in pipe.transcribe_chunked(c, sample_rate=16000).segments] for c in clips]
+    base = dict(pipe.pool.stats)
     got = [None] * 4
     errs = []
+    go = threading.Barrier(4)
 
     def work(i):
         try:
-            for _ in range(3):
+            for _ in range(6):
+                go.wait(60)             # the four callers submit together, as four uploads arriving at once would
                 got[i] = [(s.start, s.end, s.text) for s in pipe.transcribe_chunked(clips[i], sample_rate=16000).segments]
         except Exception as e:  # noqa: BLE001
             errs.append(e)
@@ -455,7 +459,82 @@ def test_one_pipeline_shared_by_four_threads(device):
     [t.join() for t in ts]
     assert not errs, errs
     assert got == want
+    st = pipe.pool.stats
+    n_win = sum(len(c) // 16000 + 1 for c in clips) * 6
+    assert st["windows"] - base["windows"] == n_win
+    print(f"four callers: {st['batches'] - base['batches']} batches for {n_win} windows, "
+          f"{st['mixed_batches'] - base['mixed_batches']} of them shared by several callers")
+    assert st["mixed_batches"] - base["mixed_batches"] > 0           # batching across callers happened
+    assert st["batches"] - base["batches"] < 4 * 6                   # fewer device steps than one per call
+    pipe.close()
     eng.close()
+
+
+def test_async_tickets_two_in_flight_equal_the_synchronous_call(device):
+    """oasr_transcribe_host_async / oasr_wait: two batches in flight (the second one's H2D under the first one's
+    forward) give exactly the synchronous results; a third submit without a wait is refused (OASR_ERR_STATE), and
+    the slots are usable again after the waits."""
+    ocfg, w, eng = make_engine("tiny80", device)
+    wave, ns = golden_inputs()
+    B, L = wave.shape
+    T = eng.feature_length(L)
+    a_in = wave.numpy().copy()
+    b_in = np.ascontiguousarray(a_in[::-1])
+    ns_b = list(reversed(ns))
+    ref_a = eng.transcribe_host(a_in, ns, normalised=False)
+    ref_b = eng.transcribe_host(b_in, ns_b, normalised=False)
+
+    def pinned(shape, dt):
+        return torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+
+    bufs = []
+    for src in (a_in, b_in):
+        x = pinned((B, L), torch.float32)
+        x[:] = src
+        bufs.append((x, pinned((B, T), torch.int32), pinned((B, T), torch.int32), pinned((B,), torch.int32)))
+    for _ in range(3):                       # slots are reused round after round
+        t0 = eng.submit_host(bufs[0][0], ns, *bufs[0][1:])
+        t1 = eng.submit_host(bufs[1][0], ns_b, *bufs[1][1:])
+        with pytest.raises(RuntimeError):
+            eng.submit_host(bufs[0][0], ns, *bufs[0][1:])
+        eng.wait(t0)
+        eng.wait(t1)
+        eng.wait(t0)                         # waiting twice is harmless
+        for (x, ids, frames, lens), ref in zip(bufs, (ref_a, ref_b)):
+            for r in range(B):
+                assert ids[r, :lens[r]].tolist() == ref.token_ids[r].tolist()
+                assert frames[r, :lens[r]].tolist() == ref.token_frames[r].tolist()
+    # PCM16 through the asynchronous entry point
+    pcm = np.clip(a_in * 8000, -32768, 32767).astype(np.int16)
+    ref_p = eng.transcribe_host(pcm, ns)
+    xp = pinned((B, L), torch.int16)
+    xp[:] = pcm
+    t = eng.submit_host(xp, ns, *bufs[0][1:])
+    eng.wait(t)
+    for r in range(B):
+        assert bufs[0][1][r, :bufs[0][3][r]].tolist() == ref_p.token_ids[r].tolist()
+    eng.close()
+
+
+def test_one_process_drives_every_gpu(device):
+    """devices="all": one pipeline object, one process, an engine and a worker thread per visible GPU (the reference's
+    caller is a process-wide singleton, workflows/wav2elan_web/app.py:38-54).  The transcript equals the one-GPU
+    transcript and every GPU served windows."""
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    ocfg = O.PRESETS["tiny"]
+    w = O.init_weights(ocfg, seed=0)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal(16000 * 40 + 777) * 0.2).astype(np.float32)
+    one = CTCASRPipeline(product_cfg(ocfg), weights=w, device=device, window_seconds=1.0, batch_windows=4, distributed=False)
+    want = [(s.start, s.end, s.text) for s in one.transcribe_chunked(x, sample_rate=16000).segments]
+    one.close()
+    pipe = CTCASRPipeline(product_cfg(ocfg), weights=w, devices="all", window_seconds=1.0, batch_windows=4, distributed=False)
+    got = [(s.start, s.end, s.text) for s in pipe.transcribe_chunked(x, sample_rate=16000).segments]
+    assert got == want
+    assert len(pipe.engines) == torch.cuda.device_count() and all(n > 0 for n in pipe.pool.stats["per_engine"])
+    pipe.close()
 
 
 def test_small_batch_graph_replay_equals_eager_launches(device):
