@@ -53,6 +53,9 @@ def parse_args():
                     help="fused: all-reduce + residual + LayerNorm as one kernel over NVLink peer memory; nccl: ncclAllReduce")
     ap.add_argument("--tp", type=int, default=1, help="tensor-parallel degree (BASELINE config 4: 7B encoder over "
                                                       "2/4/8 GPUs); must equal --gpus, every rank sees the same batch")
+    ap.add_argument("--no-tp-leg", action="store_true",
+                    help="with --gpus N >= 2: skip the short omniASR_CTC_7B tensor-parallel leg (config4_tp key)")
+    ap.add_argument("--tp-leg-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -94,6 +97,18 @@ def measured_peaks() -> tuple[dict, str]:
         except Exception:
             pass
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def kernels_sha() -> str:
+    """Content hash of the CUDA sources liboasr.so is built from: profiles/ncu_traffic.json records the hash of the
+    binary it was captured on (scripts/profile_step.sh), and a capture of other kernels is not reported as `traffic`."""
+    import hashlib
+    h = hashlib.sha256()
+    src = ROOT / "omnilingual-asr_b200" / "csrc"
+    for f in sorted(list(src.glob("*.cu")) + list(src.glob("*.cuh")) + list(src.glob("*.h"))):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -191,6 +206,69 @@ def run_reference(args):
     print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
+def tp_leg(args, dist, dev, rank, world, local):
+    """BASELINE configs[3]: omniASR_CTC_7B with the encoder split tensor-parallel over all `world` GPUs, every rank
+    feeding the same 32 x 30 s batch (peer-memory reductions, tp_fused.cu).  A few steps, reported under `config4_tp`
+    of the data-parallel line so that the driver's scaling record carries it."""
+    from omnilingual_asr.models.config import get_model_config
+    from omnilingual_asr.models.inference.ctc_engine import CtcEngine
+    from omnilingual_asr.models.weights import random_weights
+    model = "omniASR_CTC_7B"
+    cfg = get_model_config(model)
+    B, L = args.batch, int(WINDOW_SEC * SR)
+    T = cfg.feature_length(L)
+    steps = max(1, args.tp_leg_steps)
+    idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(CtcEngine.tp_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    eng = CtcEngine(cfg, device=dev, tp_rank=rank, tp_world=world, tp_id=idt.cpu().numpy().tobytes())
+    eng.tp_enable_peer_memory(B, L)
+    eng.load_state_dict(random_weights(cfg, 0, dev))
+    torch.cuda.empty_cache()
+    wave_dev = synthetic_windows(B, 1234).to(dev)
+    ns = [L] * B
+    for _ in range(2):
+        eng.forward(wave_dev, ns, return_frame_ids=False)
+    eng.profile_read()
+    eng.profile(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(steps):
+        res = eng.forward(wave_dev, ns, return_frame_ids=False)
+    ev1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    stage_ms = eng.profile_read()
+    eng.profile(False)
+    clk = clocks.stop() if rank == 0 else {}
+    eng.close()
+    fl = flops_per_window(cfg, T)
+    gemm_names = ["qkv_gemm", "outproj_gemm", "ffn1_gemm", "ffn2_gemm"]
+    g_ms = sum(stage_ms[n][0] for n in gemm_names)
+    g_flops = sum(fl[n] for n in gemm_names) * B * steps / world          # this rank's share of the contractions
+    peaks, _ = measured_peaks()
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    ach = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+    return {
+        "workload": f"{model}, {B} x 30 s synthetic windows, encoder tensor-parallel over {world} GPUs (same batch on every rank)",
+        "tp": world, "steps": steps, "warmup": 2, "ms_per_step": ms, "value": B * WINDOW_SEC / (ms / 1e3), "unit": UNIT,
+        "reduction": "bf16 partial sums; reduce-scatter + residual + LayerNorm + all-gather per half-batch on the copy "
+                     "engines beside the other half-batch's GEMMs (tp_fused.cu: tp_dma_reduce_layernorm)",
+        "stages_ms_per_step": {k: v[0] / steps for k, v in stage_ms.items() if v[1] > 0},
+        "encoder_gemm_tflops_per_gpu": ach, "encoder_gemm_frac_of_sustained_peak": ach / peak,
+        "tokens_window0": int(len(res.token_ids[0])), "clocks": clk,
+    }
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -280,6 +358,17 @@ def run_ours(args):
     h2d = B * L * 4
     d2h = 2 * B * T * 4 + B * 4
 
+    # ---------------------------------------------------------------- config 4: the 7B tensor-parallel leg
+    config4 = None
+    if world > 1 and tp == 1 and not args.no_tp_leg:
+        eng.close()
+        del wave_dev
+        torch.cuda.empty_cache()
+        try:
+            config4 = tp_leg(args, dist, dev, rank, world, local)
+        except Exception as e:  # noqa: BLE001 - the data-parallel line is still valid
+            config4 = {"error": f"{type(e).__name__}: {e}"[:400]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -295,12 +384,12 @@ def run_ours(args):
             continue
         entry = {"ms_per_step": ms / args.steps, "share": ms / total_stage_ms, "launch_groups": cnt}
         if name in fl and ms > 0:
-            entry["tflops"] = fl[name] * B * args.steps / (ms / 1e3) / 1e12
+            entry["tflops"] = fl[name] * B * args.steps / (ms / 1e3) / 1e12 / (tp if name not in ("fe_layer0", "fe_conv_1_6", "feature_proj", "posconv", "ctc_head_argmax") else 1)
         stages[name] = entry
     gemm_names = ["qkv_gemm", "outproj_gemm", "ffn1_gemm", "ffn2_gemm"]
     g_ms = sum(stage_ms[n][0] for n in gemm_names)
     g_cnt = sum(stage_ms[n][1] for n in gemm_names)
-    g_flops = sum(fl[n] for n in gemm_names) * B * args.steps
+    g_flops = sum(fl[n] for n in gemm_names) * B * args.steps / max(tp, 1)   # a tensor-parallel rank computes 1/tp of them
     achieved = g_flops / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     # DRAM bytes per launch of the same kernels from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
@@ -308,7 +397,10 @@ def run_ours(args):
     traffic, ncu_note = None, None
     try:
         tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
-        if args.model == "omniASR_CTC_1B" and B == 32:
+        if tj.get("kernels_sha") != kernels_sha():
+            ncu_note = (f"profiles/ncu_traffic.json was captured on other kernel sources ({tj.get('kernels_sha')} vs "
+                        f"{kernels_sha()}): regenerate with scripts/profile_step.sh")
+        elif args.model == "omniASR_CTC_1B" and B == 32 and tp == 1:
             per = [tj["kernels"][n]["traffic_bytes"] for n in gemm_names]
             traffic = sum(per) / len(per)
             ncu_note = {n: {"traffic_bytes": tj["kernels"][n]["traffic_bytes"],
@@ -345,6 +437,8 @@ def run_ours(args):
         "clocks": clk,
         "roofline": roofline,
     }
+    if config4 is not None:
+        line["config4_tp"] = config4
     if not args.no_cpu_baseline and world == 1:
         val, cores, times = cpu_oracle_throughput(args.model, args.cpu_windows, reps=1)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",

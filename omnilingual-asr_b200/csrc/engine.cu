@@ -187,7 +187,11 @@ struct OasrEngine {
   int tp_world = 1, tp_first = 0, tp_local = 1;
   bool tp_emulated = false;
   void* tp_comm = nullptr;
-  float* part = nullptr;            // [M, d] fp32 partial sums of the row-parallel GEMMs
+  float* part = nullptr;            // [M, d] fp32 partial sums of the row-parallel GEMMs (NCCL mode only)
+  __nv_bfloat16* part_bf16 = nullptr;   // peer-memory path: [M, d] bf16 partial sums (in the arena); emulation: [shards][M, d]
+  long long part_shard_stride = 0;  // elements between the shards' partials (emulation)
+  unsigned int* tp_err_host = nullptr;   // host-mapped error word the flag waits set on a timeout
+  unsigned int* tp_err_dev = nullptr;
   // peer-memory path (tp_fused.cu): x | ln | part | flags of this rank live in one IPC-exported arena
   void* tp_arena = nullptr;
   size_t tp_off_ln = 0, tp_off_part = 0, tp_off_flags = 0, tp_x_bytes = 0;
@@ -196,12 +200,12 @@ struct OasrEngine {
   TpPeerView tp_view2{};            // second flag set (half-batch 1 in overlap mode)
   unsigned long long tp_epoch2 = 0;
   cudaStream_t tp_comm_stream2 = nullptr;
-  float* tp_recv2 = nullptr;
+  __nv_bfloat16* tp_recv2 = nullptr;
   bool tp_fused = false;
   unsigned long long tp_epoch = 0;
   // overlap mode of the peer-memory path: the reduce kernels run on their own stream beside the other half-batch's GEMMs
   cudaStream_t tp_comm_stream = nullptr;
-  float* tp_recv = nullptr;         // copy-engine mode: the peers' partial rows of this rank's row share
+  __nv_bfloat16* tp_recv = nullptr; // copy-engine mode: the peers' partial rows of this rank's row share
   size_t tp_recv_bytes = 0;
   cudaEvent_t tp_ev_compute[2] = {nullptr, nullptr}, tp_ev_reduce[2] = {nullptr, nullptr};
   // shapes of the last forward (debug buffers)
@@ -283,8 +287,14 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   OASR_TRY(A((void**)&e->qkv, (size_t)M * 3 * d * 2, false));
   OASR_TRY(A((void**)&e->att, (size_t)M * d * 2, false));
   OASR_TRY(A((void**)&e->ffn, (size_t)M * F * 2, false));
-  if (e->tp_arena != nullptr) e->part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(e->tp_arena) + e->tp_off_part);
-  else if (e->tp_world > 1) OASR_TRY(A((void**)&e->part, (size_t)M * d * 4, false));
+  if (e->tp_arena != nullptr) {
+    e->part_bf16 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(e->tp_arena) + e->tp_off_part);
+  } else if (e->tp_emulated) {
+    e->part_shard_stride = M * d;
+    OASR_TRY(A((void**)&e->part_bf16, (size_t)e->tp_local * M * d * 2, false));
+  } else if (e->tp_world > 1) {
+    OASR_TRY(A((void**)&e->part, (size_t)M * d * 4, false));
+  }
   OASR_TRY(A((void**)&e->keys, (size_t)M * 8, true));
   OASR_TRY(A((void**)&e->n_samples_dev, (size_t)nB * 4, true));
   OASR_TRY(A((void**)&e->n_frames_dev, (size_t)nB * 4, true));
@@ -402,15 +412,15 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
   const long long M = Mh[0] + Mh[1];
   {
     const long long share = Mh[0] - (Mh[0] / W) * (W - 1);
-    const size_t need = (size_t)(W - 1) * (size_t)share * d * 4;
+    const size_t need = (size_t)(W - 1) * (size_t)share * d * 2;
     if (need > e->tp_recv_bytes) {   // one buffer per half-batch: their reductions may be in flight together
       if (e->tp_recv) cudaFree(e->tp_recv);
       e->tp_recv = nullptr;
       e->tp_recv_bytes = 0;
       void* ptr = nullptr;
       OASR_TRY(dev_alloc(&ptr, 2 * need, false));
-      e->tp_recv = reinterpret_cast<float*>(ptr);
-      e->tp_recv2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ptr) + need);
+      e->tp_recv = reinterpret_cast<__nv_bfloat16*>(ptr);
+      e->tp_recv2 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ptr) + need);
       e->tp_recv_bytes = need;
     }
   }
@@ -466,9 +476,9 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       {
         GemmArgs a = GemmArgs::plain(e->att + r0[h] * d_loc, (int)Mh[h], d_loc, d_loc, w.s_wo[0], d);
         a.bias = add_bias ? w.bo : nullptr;
-        a.out = e->part + r0[h] * d;
+        a.out = e->part_bf16 + r0[h] * d;   // this rank's partial sum, rounded to bf16: what crosses NVLink
         a.ldo = d;
-        a.epilogue = EPI_F32;
+        a.epilogue = EPI_BF16;
         OASR_TRY(gemm_bf16_tcgen05(a, st));
       }
       OASR_TRY(reduce_ln(h, w.ffn_ln_g, w.ffn_ln_b, false));
@@ -494,9 +504,9 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       {
         GemmArgs a = GemmArgs::plain(e->ffn + r0[h] * F_loc, (int)Mh[h], F_loc, F_loc, w.s_w2[0], d);
         a.bias = add_bias ? w.b2 : nullptr;
-        a.out = e->part + r0[h] * d;
+        a.out = e->part_bf16 + r0[h] * d;
         a.ldo = d;
-        a.epilogue = EPI_F32;
+        a.epilogue = EPI_BF16;
         OASR_TRY(gemm_bf16_tcgen05(a, st));
       }
       OASR_TRY(reduce_ln(h, g, bta, want_hidden));
@@ -530,6 +540,15 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
 }
 
 
+// A flag wait of the peer-memory path that ran out of time leaves its mark in host-mapped memory (tp_fused.cu): the
+// group is out of step from then on, so every later call fails until the engines are rebuilt.
+int tp_check_error(OasrEngine* e) {
+  if (e->tp_err_host != nullptr && *reinterpret_cast<volatile unsigned int*>(e->tp_err_host) != 0)
+    return fail(OASR_ERR_STATE, "tensor parallelism: a peer rank did not reach a reduction within OASR_TP_TIMEOUT_MS "
+                                "(ranks must run the same batches in the same order); rebuild the group's engines");
+  return OASR_OK;
+}
+
 // window lengths -> device (pinned staging slots, so that the copies are asynchronous and a slot is not rewritten
 // before its copy has run)
 int stage_lengths(OasrEngine* e, const int32_t* n_samples_host, int B, int L, cudaStream_t st) {
@@ -557,6 +576,7 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
                   int flags, int stop_stage, float* hidden_out, bool staged, cudaStream_t st) {
   if (!e->finalized) return fail(OASR_ERR_STATE, "oasr_finalize_weights has not been called");
   OASR_REQUIRE(wave_in && n_samples_host && B > 0 && L > 0, "forward: bad arguments");
+  OASR_TRY(tp_check_error(e));
   const OasrConfig& c = e->cfg;
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
   OASR_TRY(ensure_workspace(e, B, L));
@@ -642,15 +662,14 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
 
   // a14
   const float scale = 1.0f / sqrtf((float)hd);
-  // OASR_TP_OVERLAP = dma: the reductions' transfers run on the copy engines beside the other half-batch's GEMMs
-  // (default for two ranks, the configuration verified on hardware) | off: one fused peer-memory kernel per reduction,
-  // nothing beside it (default for more than two ranks)
+  // OASR_TP_OVERLAP = dma (default): the reductions' transfers run on the copy engines beside the other half-batch's
+  // GEMMs | off: one fused peer-memory kernel per reduction, nothing beside it (also what a single window takes)
   static const int tp_overlap = [] {
     const char* v = std::getenv("OASR_TP_OVERLAP");
     if (v == nullptr) return -1;
     return std::strcmp(v, "dma") == 0 ? 1 : 0;
   }();
-  const bool overlap = tp_overlap < 0 ? e->tp_world == 2 : tp_overlap == 1;
+  const bool overlap = tp_overlap < 0 ? true : tp_overlap == 1;
   if (e->tp_world > 1 && e->tp_fused && e->tp_local == 1 && B >= 2 && c.n_layers > 0 && overlap) {
     OASR_TRY(tp_layers_overlapped(e, B, T, hidden_out, stop_stage, st));
     if (stop_stage >= 4 && stop_stage < 4 + c.n_layers) {
@@ -661,6 +680,14 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
     // Tensor-parallel layers: q/k/v + attention + FFN1 on this rank's heads / hidden columns, out-proj and FFN2 as
     // partial sums over the local input columns -> all-reduce -> residual add fused into the next LayerNorm pass.
     const int W = e->tp_world, d_loc = d / W, F_loc = F / W, H_loc = H / W;
+    // peer-memory runs and the one-GPU emulation of the split keep every shard's partial sum in bf16 and add them in
+    // rank order (tp_fused.cu); the NCCL mode all-reduces fp32 partial sums
+    const bool bf16_part = e->tp_fused || e->tp_emulated;
+    auto emulated_reduce = [&](const float* g, const float* bta) -> int {
+      const __nv_bfloat16* parts[TP_MAX_WORLD];
+      for (int s = 0; s < e->tp_local; ++s) parts[s] = e->part_bf16 + s * e->part_shard_stride;
+      return tp_local_reduce_layernorm(e->x, parts, e->tp_local, M, d, g, bta, e->lnbuf, st);
+    };
     auto reduce_partial = [&]() -> int {
       if (e->tp_comm != nullptr) {
         prof_mark(e, OASR_PROF_ALLREDUCE, st);
@@ -691,10 +718,15 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
         {
           GemmArgs a = GemmArgs::plain(e->att, (int)M, d_loc, d_loc, w.s_wo[s], d);
           a.bias = add_bias ? w.bo : nullptr;
-          a.out = e->part;
           a.ldo = d;
-          a.resid = first ? nullptr : e->part;
-          a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          if (bf16_part) {   // every shard's partial sum on its own, rounded to bf16 (what crosses NVLink in a real run)
+            a.out = e->part_bf16 + s * e->part_shard_stride;
+            a.epilogue = EPI_BF16;
+          } else {
+            a.out = e->part;
+            a.resid = first ? nullptr : e->part;
+            a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          }
           OASR_TRY(gemm_bf16_tcgen05(a, st));
         }
         e->launches += 3;
@@ -702,6 +734,9 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
       if (e->tp_fused) {   // all-reduce + residual + LayerNorm + redistribution in one kernel over peer memory
         prof_mark(e, OASR_PROF_ALLREDUCE, st);
         OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, w.ffn_ln_g, w.ffn_ln_b, ++e->tp_epoch, false, st));
+      } else if (e->tp_emulated) {
+        prof_mark(e, OASR_PROF_ALLREDUCE, st);
+        OASR_TRY(emulated_reduce(w.ffn_ln_g, w.ffn_ln_b));
       } else {
         OASR_TRY(reduce_partial());
         prof_mark(e, OASR_PROF_LAYERNORM, st);
@@ -723,10 +758,15 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
         {
           GemmArgs a = GemmArgs::plain(e->ffn, (int)M, F_loc, F_loc, w.s_w2[s], d);
           a.bias = add_bias ? w.b2 : nullptr;
-          a.out = e->part;
           a.ldo = d;
-          a.resid = first ? nullptr : e->part;
-          a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          if (bf16_part) {
+            a.out = e->part_bf16 + s * e->part_shard_stride;
+            a.epilogue = EPI_BF16;
+          } else {
+            a.out = e->part;
+            a.resid = first ? nullptr : e->part;
+            a.epilogue = first ? EPI_F32 : EPI_F32_RESID;
+          }
           OASR_TRY(gemm_bf16_tcgen05(a, st));
         }
         e->launches += 2;
@@ -740,6 +780,13 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
         const bool want_hidden = last && hidden_out != nullptr;   // parity runs: the fp32 LayerNorm output of all rows
         OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, g, bta, ++e->tp_epoch, want_hidden, st));
         if (want_hidden) {
+          prof_mark(e, OASR_PROF_LAYERNORM, st);
+          OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, hidden_out, st));
+        }
+      } else if (e->tp_emulated) {
+        prof_mark(e, OASR_PROF_ALLREDUCE, st);
+        OASR_TRY(emulated_reduce(g, bta));
+        if (last && hidden_out != nullptr) {
           prof_mark(e, OASR_PROF_LAYERNORM, st);
           OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, hidden_out, st));
         }
@@ -893,6 +940,7 @@ void oasr_destroy(OasrHandle h) {
   for (size_t q = 0; q < h->tp_peer_base.size(); ++q)
     if ((int)q != h->tp_first && h->tp_peer_base[q]) cudaIpcCloseMemHandle(h->tp_peer_base[q]);
   if (h->tp_arena) cudaFree(h->tp_arena);
+  if (h->tp_err_host) cudaFreeHost(h->tp_err_host);
   for (auto& g : h->graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
@@ -1025,6 +1073,7 @@ int oasr_tp_init(OasrHandle h, int32_t rank, int32_t world, const void* id) {
 int oasr_tp_emulate(OasrHandle h, int32_t world) {
   OASR_TRY(tp_check_split(h, world));
   if (h->tp_comm != nullptr || h->tp_world != 1) return fail(OASR_ERR_STATE, "tensor parallelism already initialised");
+  if (world > TP_MAX_WORLD) return fail(OASR_ERR_UNSUPPORTED, "at most 8 tensor-parallel shards");
   h->tp_world = world;
   h->tp_first = 0;
   h->tp_local = world;
@@ -1045,7 +1094,7 @@ int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out) {
   h->tp_x_bytes = M * d * 4;
   h->tp_off_ln = up(h->tp_x_bytes);
   h->tp_off_part = h->tp_off_ln + up(M * std::max<size_t>(512, d) * 2);
-  h->tp_off_flags = h->tp_off_part + up(M * d * 4);
+  h->tp_off_flags = h->tp_off_part + up(M * d * 2);   // partial sums travel in bf16
   const size_t total = h->tp_off_flags + 1024;   // two flag sets, 512 B apart (one per half-batch in overlap mode)
   OASR_TRY(dev_alloc(&h->tp_arena, total, true));
   OASR_CUDA_CHECK(cudaDeviceSynchronize());
@@ -1078,11 +1127,18 @@ int oasr_tp_ipc_import(OasrHandle h, const void* handles) {
     uint8_t* base = reinterpret_cast<uint8_t*>(h->tp_peer_base[q]);
     v.x[q] = reinterpret_cast<float*>(base);
     v.ln[q] = reinterpret_cast<__nv_bfloat16*>(base + h->tp_off_ln);
-    v.part[q] = reinterpret_cast<const float*>(base + h->tp_off_part);
+    v.part[q] = reinterpret_cast<const __nv_bfloat16*>(base + h->tp_off_part);
     v.ready[q] = reinterpret_cast<unsigned long long*>(base + h->tp_off_flags);
     v.done[q] = v.ready[q] + TP_MAX_WORLD;
   }
   v.cta_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(h->tp_arena) + h->tp_off_flags + 2 * TP_MAX_WORLD * 8);
+  if (h->tp_err_host == nullptr) {
+    OASR_CUDA_CHECK(cudaHostAlloc((void**)&h->tp_err_host, 64, cudaHostAllocMapped));
+    *h->tp_err_host = 0;
+    OASR_CUDA_CHECK(cudaHostGetDevicePointer((void**)&h->tp_err_dev, h->tp_err_host, 0));
+  }
+  v.error = h->tp_err_dev;
+  v.timeout_ns = tp_timeout_ns();
   h->tp_view2 = v;   // the second flag set: same buffers, flags 512 B further on
   for (int q = 0; q < W; ++q) {
     h->tp_view2.ready[q] = v.ready[q] + 64;
@@ -1356,7 +1412,7 @@ int oasr_wait(OasrHandle h, int64_t ticket) {
   e->slot_busy[slot] = false;                // only now may a submit reuse the slot's landing buffer
   if (ce != cudaSuccess) return fail(OASR_ERR_CUDA, std::string("oasr_wait: ") + cudaGetErrorString(ce));
   if (e->slot_lens_host[slot] != nullptr) memset(e->slot_lens_host[slot], 0, (size_t)e->slot_B[slot] * 4);
-  return OASR_OK;
+  return tp_check_error(e);
 }
 
 int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stride, const int32_t* n_samples_host,
@@ -1392,6 +1448,7 @@ int oasr_transcribe_host(OasrHandle h, const float* wave_host, int64_t wave_stri
   }
   ce = cudaStreamSynchronize(st);
   if (rc == OASR_OK && ce != cudaSuccess) rc = fail(OASR_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(ce));
+  if (rc == OASR_OK) rc = tp_check_error(h);
   return rc;
 }
 

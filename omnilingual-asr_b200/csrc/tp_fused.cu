@@ -3,16 +3,22 @@
 // Replaces ncclAllReduce(part) followed by the add+LayerNorm pass.  Rank r owns the rows [r M/W, (r+1) M/W): for each
 // of them it reads x (local) and the W partial rows (one local, W-1 over NVLink: plain ld.global on peer pointers
 // mapped with CUDA IPC), and writes the new fp32 residual row and the bf16 LayerNorm row into EVERY rank's buffers
-// (peer st.global).  The fp32 residual stream itself stays row-sharded (only a row's owner ever adds to it), so per rank
-// and call (W-1)/W of |part| comes in and (W-1)/W of |ln| (bf16) goes out over NVLink: 294 MB for the 7B shape at
-// W = 2, against 786 MB for an fp32 ring all-reduce - and the separate add + LayerNorm pass over HBM disappears.
+// (peer st.global).  The fp32 residual stream itself stays row-sharded (only a row's owner ever adds to it), and the
+// partial sums are rounded to bf16 by the GEMM epilogue that produces them (the oracle rounds at the same point:
+// ctc_oracle._row_parallel_linear), so per rank and call (W-1)/W of |part| (bf16) comes in and (W-1)/W of |ln| (bf16)
+// goes out over NVLink: 196 MB for the 7B shape at W = 2, against 786 MB for an fp32 ring all-reduce - and the separate
+// add + LayerNorm pass over HBM disappears.  The sum is taken in fp32 in rank order on every rank: deterministic.
 //
 // Cross-GPU ordering uses two monotonically increasing flags per (rank, peer) in peer memory:
 //   ready[src] = e   "src's partial sums of call e are complete"   signalled by CTA 0 at kernel start (the GEMM that
 //                    produced them precedes this kernel on src's stream), awaited by every CTA before its first peer read;
 //   done[src]  = e   "src has written its rows of call e everywhere" signalled by the last CTA to finish after a
 //                    system-scope fence, awaited by tp_wait_kernel before the next GEMM of the stream reads LN(x).
-// No kernel waits for a kernel of the SAME GPU; every wait is bounded (trap, not hang).
+// No kernel waits for a kernel of the SAME GPU.  Every wait is bounded by OASR_TP_TIMEOUT_MS of %globaltimer (default
+// 60 s: ranks are separate processes and may be skewed by a first-call allocation, host-side audio loading or a
+// profiler attaching); on expiry the kernel sets this rank's host-mapped error word and carries on with whatever is
+// there - the engine reports OASR_ERR_STATE at its next check instead of losing the context to a trap.  The host is
+// expected to start the forward of a batch on all ranks of the group together (same batch, same order).
 //
 // tp_dma_reduce_layernorm (end of this file) is the same reduction with the NVLink transfers on the copy engines and
 // only the add + LayerNorm of this rank's rows on SMs (tp_reduce_ln_kernel on all-local pointers, barriers = 0); the
@@ -22,10 +28,10 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 namespace oasr {
 namespace {
-
-constexpr long long SPIN_TIMEOUT_CYCLES = 6000000000ll;   // ~3 s
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -35,14 +41,29 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void spin_until(const unsigned long long* flag, unsigned long long epoch) {
-  const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// false: the peer did not arrive in time (the error word is set; the caller goes on so that the stream drains)
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long epoch, const TpPeerView& P) {
+  if (ld_acquire_sys(flag) >= epoch) return true;
+  const unsigned long long t0 = global_ns();
   while (ld_acquire_sys(flag) < epoch) {
-    if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
-      printf("oasr: tensor-parallel flag timeout (block %d, flag %p, want %llu)\n", blockIdx.x, (const void*)flag, epoch);
-      __trap();
+    if (*reinterpret_cast<volatile unsigned int*>(P.error) != 0) return false;   // this rank has given up already
+    if (global_ns() - t0 > P.timeout_ns) {
+      *reinterpret_cast<volatile unsigned int*>(P.error) = 1u;
+      __threadfence_system();
+      return false;
     }
   }
+  return true;
+}
+__device__ __forceinline__ float4 bf16x4_to_f32(uint2 u) {
+  const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -54,9 +75,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// MAXJ: float4 groups of a row per lane (row in registers); AJ: groups of a partial row requested at a time.  The
-// peer-memory launch asks for whole partial rows (AJ = MAXJ: most bytes in flight over NVLink, at the price of spills
-// at D = 2048); the all-local launch of the copy-engine path takes them in two halves and stays within 128 registers.
+// MAXJ: float4 groups of a row per lane (row in registers); AJ: 4-element groups of a bf16 partial row requested at a
+// time (8 bytes per lane and group).  Whole partial rows are requested at once: most bytes in flight over NVLink.
 template <int MAXJ, int AJ>
 __global__ void __launch_bounds__(256, 2)
 tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, const float* __restrict__ gamma,
@@ -65,7 +85,7 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
   if (barriers && threadIdx.x == 0) {
     if (blockIdx.x == 0)
       for (int q = 0; q < P.world; ++q) st_release_sys(P.ready[q] + P.rank, epoch);
-    for (int q = 0; q < P.world; ++q) spin_until(P.ready[P.rank] + q, epoch);
+    for (int q = 0; q < P.world; ++q) spin_until(P.ready[P.rank] + q, epoch, P);
   }
   __syncthreads();
 
@@ -83,18 +103,19 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
       for (int j = 0; j < MAXJ; ++j)
         if (lane + 32 * j < ngroups) v[j] = xs[lane + 32 * j];
     }
-    for (int q = 0; q < P.world; ++q) {   // partial sums: local and peer rows
-      const float4* ps = reinterpret_cast<const float4*>(P.part[q] + row * D);
+    for (int q = 0; q < P.world; ++q) {   // partial sums in rank order: local and peer rows, bf16
+      const uint2* ps = reinterpret_cast<const uint2*>(P.part[q] + row * D);
 #pragma unroll
       for (int j0 = 0; j0 < MAXJ; j0 += AJ) {
-        float4 a[AJ];
+        uint2 a[AJ];
 #pragma unroll
         for (int j = 0; j < AJ; ++j)
           if (j0 + j < MAXJ && lane + 32 * (j0 + j) < ngroups) a[j] = ps[lane + 32 * (j0 + j)];
 #pragma unroll
         for (int j = 0; j < AJ; ++j)
           if (j0 + j < MAXJ && lane + 32 * (j0 + j) < ngroups) {
-            v[j0 + j].x += a[j].x; v[j0 + j].y += a[j].y; v[j0 + j].z += a[j].z; v[j0 + j].w += a[j].w;
+            const float4 f = bf16x4_to_f32(a[j]);
+            v[j0 + j].x += f.x; v[j0 + j].y += f.y; v[j0 + j].z += f.z; v[j0 + j].w += f.w;
           }
       }
     }
@@ -150,8 +171,8 @@ tp_reduce_ln_kernel(const TpPeerView P, long long row0, long long nrows, int D, 
   }
 }
 
-__global__ void tp_wait_kernel(const unsigned long long* done_flags, int world, unsigned long long epoch) {
-  if (threadIdx.x < world) spin_until(done_flags + threadIdx.x, epoch);
+__global__ void tp_wait_kernel(const TpPeerView P, unsigned long long epoch) {
+  if ((int)threadIdx.x < P.world) spin_until(P.done[P.rank] + threadIdx.x, epoch, P);
 }
 
 // thread q tells rank q that this rank has reached `epoch` (which = 0: P.ready, 1: P.done), then waits until rank q
@@ -160,7 +181,7 @@ __global__ void tp_signal_wait_kernel(const TpPeerView P, int which, unsigned lo
   if ((int)threadIdx.x < P.world) {
     __threadfence_system();
     st_release_sys((which == 0 ? P.ready[threadIdx.x] : P.done[threadIdx.x]) + P.rank, epoch);
-    spin_until((which == 0 ? P.ready[P.rank] : P.done[P.rank]) + threadIdx.x, epoch);
+    spin_until((which == 0 ? P.ready[P.rank] : P.done[P.rank]) + threadIdx.x, epoch, P);
   }
 }
 
@@ -177,7 +198,7 @@ int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, 
   else if (D <= 1280) tp_reduce_ln_kernel<10, 10><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
   else tp_reduce_ln_kernel<16, 16><<<grid, 256, 0, stream>>>(P, row0, nrows, D, gamma, beta, epoch, bcast_x ? 1 : 0, 1);
   // the next kernel on this stream reads LN(x) written by every rank
-  tp_wait_kernel<<<1, 32, 0, stream>>>(P.done[P.rank], P.world, epoch);
+  tp_wait_kernel<<<1, 32, 0, stream>>>(P, epoch);
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
 }
@@ -187,11 +208,11 @@ int tp_fused_reduce_layernorm(const TpPeerView& P, long long rows_total, int D, 
 //   signal ready + wait for every rank's ready (one kernel) -> DMA the peers' partial rows of MY row share into `recv`
 //   -> local kernel: x += sum of the partials, LayerNorm -> DMA my LayerNorm rows (and x rows if bcast_x) to every
 //   peer -> signal done -> wait for every rank's done.
-// recv: [(world - 1)][rows_share_max * D] fp32, local.  A peer reads this rank's partial rows between its `ready`
+// recv: [(world - 1)][rows_share_max * D] bf16, local.  A peer reads this rank's partial rows between its `ready`
 // wait and its `done` signal, so the caller may overwrite them once this call's stream work has completed.
 int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long rows_total, int D, const float* gamma,
-                            const float* beta, unsigned long long epoch, bool bcast_x, float* recv, cudaStream_t stream,
-                            cudaEvent_t* trace) {
+                            const float* beta, unsigned long long epoch, bool bcast_x, __nv_bfloat16* recv,
+                            cudaStream_t stream, cudaEvent_t* trace) {
   OASR_REQUIRE(P.world >= 2 && P.world <= TP_MAX_WORLD && D % 4 == 0 && D <= 2048 && recv != nullptr,
                "tp_dma: bad arguments");
   int trace_i = 0;
@@ -212,9 +233,9 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
     L.x[q] = P.x[P.rank];
     L.ln[q] = P.ln[P.rank];
     if (q == P.rank) continue;
-    float* dst = recv + (size_t)slot * (size_t)(rows_total - per * (P.world - 1)) * D;   // a slot holds the largest share
+    __nv_bfloat16* dst = recv + (size_t)slot * (size_t)(rows_total - per * (P.world - 1)) * D;   // a slot holds the largest share
     if (nrows > 0)
-      OASR_CUDA_CHECK(cudaMemcpyAsync(dst, P.part[q] + row0 * D, (size_t)nrows * D * 4, cudaMemcpyDeviceToDevice, stream));
+      OASR_CUDA_CHECK(cudaMemcpyAsync(dst, P.part[q] + row0 * D, (size_t)nrows * D * 2, cudaMemcpyDeviceToDevice, stream));
     L.part[q] = dst - row0 * D;   // the kernel indexes partials by absolute row
     ++slot;
   }
@@ -223,9 +244,9 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
     const unsigned grid = (unsigned)((nrows + 7) / 8);
     // the local view writes each LN row `world` times to the same place; world = 1 for the stores is expressed by
     // pointing every ln / x entry at the local buffers (idempotent)
-    if (D <= 512) tp_reduce_ln_kernel<4, 2><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
-    else if (D <= 1280) tp_reduce_ln_kernel<10, 5><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
-    else tp_reduce_ln_kernel<16, 8><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    if (D <= 512) tp_reduce_ln_kernel<4, 4><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else if (D <= 1280) tp_reduce_ln_kernel<10, 10><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
+    else tp_reduce_ln_kernel<16, 16><<<grid, 256, 0, stream>>>(L, row0, nrows, D, gamma, beta, epoch, 0, 0);
     stamp();
     for (int q = 0; q < P.world; ++q) {
       if (q == P.rank) continue;
@@ -241,6 +262,35 @@ int tp_dma_reduce_layernorm(const TpPeerView& P, long long first_row, long long 
   stamp();
   OASR_CUDA_CHECK(cudaGetLastError());
   return OASR_OK;
+}
+
+int tp_local_reduce_layernorm(float* x, const __nv_bfloat16* const* parts, int nparts, long long rows, int D,
+                              const float* gamma, const float* beta, __nv_bfloat16* ln, cudaStream_t stream) {
+  OASR_REQUIRE(x && parts && ln && nparts >= 1 && nparts <= TP_MAX_WORLD && D % 4 == 0 && D <= 2048, "tp_local: bad arguments");
+  if (rows <= 0) return OASR_OK;
+  TpPeerView L{};
+  L.rank = 0;
+  L.world = nparts;
+  for (int q = 0; q < nparts; ++q) {
+    L.x[q] = x;
+    L.ln[q] = ln;
+    L.part[q] = parts[q];
+  }
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (D <= 512) tp_reduce_ln_kernel<4, 4><<<grid, 256, 0, stream>>>(L, 0, rows, D, gamma, beta, 0, 0, 0);
+  else if (D <= 1280) tp_reduce_ln_kernel<10, 10><<<grid, 256, 0, stream>>>(L, 0, rows, D, gamma, beta, 0, 0, 0);
+  else tp_reduce_ln_kernel<16, 16><<<grid, 256, 0, stream>>>(L, 0, rows, D, gamma, beta, 0, 0, 0);
+  OASR_CUDA_CHECK(cudaGetLastError());
+  return OASR_OK;
+}
+
+unsigned long long tp_timeout_ns() {
+  static const unsigned long long v = [] {
+    const char* e = std::getenv("OASR_TP_TIMEOUT_MS");
+    const long long ms = e != nullptr ? std::atoll(e) : 60000;
+    return (unsigned long long)(ms > 0 ? ms : 60000) * 1000000ull;
+  }();
+  return v;
 }
 
 }  // namespace oasr

@@ -261,11 +261,29 @@ def feature_extractor(w: Dict[str, torch.Tensor], wave: torch.Tensor, cfg: CtcMo
     return x.transpose(1, 2).contiguous()
 
 
+def _row_parallel_linear(x: torch.Tensor, a: torch.Tensor, wt: torch.Tensor, bias: torch.Tensor, tp_world: int) -> torch.Tensor:
+    """Tensor-parallel row-parallel linear as the engine computes it (engine.cu, tp_fused.cu): rank r multiplies its
+    slice of the input columns (rank 0 adds the bias), rounds its PARTIAL SUM to bf16 - the partial sums cross NVLink
+    in bf16 - and the partials are added to the fp32 residual row x in rank order.  Returns the new x."""
+    K = a.shape[-1]
+    step = K // tp_world
+    out = x
+    for r in range(tp_world):
+        part = F.linear(a[..., r * step:(r + 1) * step], wt[:, r * step:(r + 1) * step], bias if r == 0 else None)
+        out = out + _q(part, True)
+    return out
+
+
 def forward(w: Dict[str, torch.Tensor], wave: torch.Tensor, n_samples: Sequence[int],
             cfg: CtcModelConfig, *, emulate_bf16: bool = False, return_logits: bool = False,
-            taps: bool = False) -> OracleOutput:
-    """Full path a9-a15 on already-normalised, zero-padded windows `wave` [B, L]."""
+            taps: bool = False, tp_world: int = 1) -> OracleOutput:
+    """Full path a9-a15 on already-normalised, zero-padded windows `wave` [B, L].
+
+    tp_world > 1 (with emulate_bf16): the rounding points of the tensor-parallel engine (BASELINE config 4) - the
+    out-proj and FFN2 partial sums of each rank are rounded to bf16 before they are added (_row_parallel_linear)."""
     q = emulate_bf16
+    if tp_world > 1 and not q:
+        raise ValueError("tp_world only changes the bf16-operand emulation")
     B = wave.shape[0]
     d, H, hd = cfg.d_model, cfg.n_heads, cfg.head_dim
     n_frames = [feature_length(int(n), cfg) for n in n_samples]
@@ -321,10 +339,16 @@ def forward(w: Dict[str, torch.Tensor], wave: torch.Tensor, n_samples: Sequence[
             a = torch.matmul(torch.softmax(s, dim=-1), vh)
         a = torch.nan_to_num(a)                         # fully padded windows
         a = _q(a.transpose(1, 2).reshape(B, T, d), q)
-        x = x + F.linear(a, _q(w[p + "o.weight"], q), w[p + "o.bias"])
+        if tp_world > 1:
+            x = _row_parallel_linear(x, a, _q(w[p + "o.weight"], q), w[p + "o.bias"], tp_world)
+        else:
+            x = x + F.linear(a, _q(w[p + "o.weight"], q), w[p + "o.bias"])
         h = _q(F.layer_norm(x, (d,), w[p + "ffn_ln.weight"], w[p + "ffn_ln.bias"], LN_EPS), q)
         h = _q(F.gelu(F.linear(h, _q(w[p + "ffn1.weight"], q), w[p + "ffn1.bias"])), q)
-        x = x + F.linear(h, _q(w[p + "ffn2.weight"], q), w[p + "ffn2.bias"])
+        if tp_world > 1:
+            x = _row_parallel_linear(x, h, _q(w[p + "ffn2.weight"], q), w[p + "ffn2.bias"], tp_world)
+        else:
+            x = x + F.linear(h, _q(w[p + "ffn2.weight"], q), w[p + "ffn2.bias"])
         if taps:
             tp[f"enc.{l}"] = x.clone()
     hidden = F.layer_norm(x, (d,), w["final_ln.weight"], w["final_ln.bias"], LN_EPS)

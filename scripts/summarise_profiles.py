@@ -96,5 +96,50 @@ def full():
     print((DST / f"{TAG}_full_summary.csv").read_text())
 
 
+def traffic():
+    """profiles/ncu_traffic.json: DRAM bytes and tensor-pipe activity per captured launch, keyed by the stage the
+    launch belongs to (scripts/profile_step.sh captures the first 17 kernels of a step, in this order), stamped with
+    the content hash of the kernel sources so that bench.py only reports a `traffic` measured on the current kernels."""
+    import json
+    sys.path.insert(0, str(ROOT))
+    import bench
+    f = DST / f"{TAG}_full_summary.csv"
+    if not f.exists():
+        return
+    rows = list(csv.reader(f.read_text().splitlines()))
+    head, rows = rows[0], rows[1:]
+    col = {h.split(" [")[0]: i for i, h in enumerate(head)}
+    order = ["fe_layer0", "fe_conv_layer1", "fe_conv_layer2", "fe_conv_layer3", "fe_conv_layer4", "fe_conv_layer5",
+             "fe_conv_layer6", "layernorm_proj", "feature_proj", "posconv", "layernorm_attn", "qkv_gemm", "attention",
+             "outproj_gemm", "layernorm_ffn", "ffn1_gemm", "ffn2_gemm"]
+    if len(rows) < len(order):
+        print(f"traffic: only {len(rows)} captured launches, expected {len(order)}; ncu_traffic.json not written")
+        return
+
+    def num(r, k):
+        return float(r[col[k]].replace(",", ""))
+
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    units = {h.split(" [")[0]: h.split(" [")[1].rstrip("]") if " [" in h else "" for h in head}
+    tens = "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"
+    kernels = {}
+    for name, r in zip(order, rows):
+        rd = num(r, "dram__bytes_read.sum") * unit_scale.get(units["dram__bytes_read.sum"], 1.0)
+        wr = num(r, "dram__bytes_write.sum") * unit_scale.get(units["dram__bytes_write.sum"], 1.0)
+        dur = num(r, "gpu__time_duration.sum")
+        du = units["gpu__time_duration.sum"]
+        dur_us = dur / 1e3 if du.startswith("n") else (dur if du.startswith("u") else dur * 1e3)
+        kernels[name] = {"kernel": r[1], "dram_read_bytes": rd, "dram_write_bytes": wr, "traffic_bytes": rd + wr,
+                         "duration_us": dur_us, "tensor_pipe_active_pct": num(r, tens) if tens in col else None,
+                         "xu_pipe_pct": num(r, "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")
+                         if "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active" in col else None}
+    out = {"source": f"profiles/{TAG}_full_summary.csv (ncu --set full --clock-control none, one launch each, "
+                     "omniASR_CTC_1B, 32 x 30 s; scripts/profile_step.sh)",
+           "kernels_sha": bench.kernels_sha(), "kernels": kernels}
+    (DST / "ncu_traffic.json").write_text(json.dumps(out, indent=1) + "\n")
+    print(f"ncu_traffic.json written for kernel sources {out['kernels_sha']}")
+
+
 launches()
 full()
+traffic()

@@ -1,5 +1,9 @@
-"""Tensor-parallel parity over NCCL: every rank runs its slice of the encoder, rank 0 compares with an unsplit engine.
-    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_check.py [preset] [fused|nccl]"""
+"""Tensor-parallel parity on N GPUs: every rank runs its slice of the encoder; rank 0 compares the result with the CPU
+ORACLE computed with the tensor-parallel rounding points (bf16-operand emulation, partial sums rounded to bf16 and
+added in rank order: ctc_oracle.forward(tp_world=N)) and with an unsplit engine.
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 scripts/tp_check.py [preset] [fused|nccl] [B]
+B > 3 repeats the golden windows (with different lengths) so that the half-batch pipeline of the peer-memory path has
+work for both halves."""
 import os
 import sys
 from pathlib import Path
@@ -25,6 +29,17 @@ ocfg = O.PRESETS[name]
 cfg = CtcModelConfig(ocfg.name, ocfg.d_model, ocfg.n_layers, ocfg.n_heads, ocfg.d_ffn, vocab=ocfg.vocab, pos_groups=ocfg.pos_groups)
 w = O.init_weights(ocfg, seed=0)
 wave, ns = golden_inputs()
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+if reps > 1:                       # a longer, still ragged batch: copies of the golden windows cut to other lengths
+    waves, nss = [], []
+    for k in range(reps):
+        wk = wave.clone()
+        nk = [max(400, n - 517 * k) for n in ns]
+        for b, n in enumerate(nk):
+            wk[b, n:] = 0
+        waves.append(wk)
+        nss += nk
+    wave, ns = torch.cat(waves), nss
 
 idt = torch.zeros(128, dtype=torch.uint8, device=dev)
 if rank == 0:
@@ -51,7 +66,20 @@ if rank == 0:
     err = max(float((res.hidden[b, :nf] - r0.hidden[b, :nf]).norm() / r0.hidden[b, :nf].norm()) for b, nf in enumerate(r0.n_frames))
     same = float(np.mean([np.mean(res.frame_ids[b, :nf] == r0.frame_ids[b, :nf]) for b, nf in enumerate(r0.n_frames)]))
     print(f"tp{world} {name} [{mode}]: hidden rel err vs unsplit {err:.2e}, frame-id agreement {same:.4f}")
-    assert err < 5e-3 and same >= 0.97
+    assert err < 8e-3 and same >= 0.95      # the unsplit engine does not round partial sums: one bf16 rounding apart
+    # the oracle with this run's rounding points (the NCCL mode sums fp32 partials: plain bf16-operand emulation)
+    emu = O.forward(w, wave, ns, ocfg, emulate_bf16=True, return_logits=True, tp_world=world if mode == "fused" else 1)
+    margin = O.top2_margin(emu.logits)
+    tot = ok = tot_all = ok_all = 0
+    e_or = 0.0
+    for b, nf in enumerate(emu.n_frames):
+        eq = res.frame_ids[b, :nf] == emu.frame_ids[b, :nf].numpy()
+        keep = (margin[b, :nf] > 0.05).numpy()
+        tot += int(keep.sum()); ok += int(eq[keep].sum()); tot_all += nf; ok_all += int(eq.sum())
+        e_or = max(e_or, float((res.hidden[b, :nf].cpu() - emu.hidden[b, :nf]).norm() / emu.hidden[b, :nf].norm()))
+    print(f"tp{world} {name} [{mode}]: vs ORACLE (tp rounding points): ids {ok_all}/{tot_all}, on margin>0.05 {ok}/{tot}, "
+          f"hidden rel err {e_or:.2e}")
+    assert ok == tot and e_or < 8e-3
     print("TP OK")
 dist.barrier()
 dist.destroy_process_group()

@@ -344,9 +344,10 @@ def test_wide_3b_7b_shapes_two_layers(device):
 @pytest.mark.parametrize("name,world", [("tiny", 2), ("tiny", 4), ("wide2l", 8)])
 def test_tensor_parallel_slicing_emulated_on_one_gpu(device, name, world):
     """Config 4's Megatron split (q/k/v + FFN1 by output columns, out-proj + FFN2 by input columns, partial sums added
-    to the fp32 residual stream inside the next LayerNorm pass) with all `world` shards computed by ONE handle and
-    summed locally: same kernels and slices as the multi-GPU run minus the NCCL all-reduce (tests/test_tp_multi_gpu.py
-    covers that on >= 2 GPUs).  Must agree with the unsplit engine up to fp32 summation order."""
+    to the fp32 residual stream inside the next LayerNorm pass) with all `world` shards computed by ONE handle: same
+    GEMMs, slices and reduction kernel (bf16 partial sums added in rank order) as the multi-GPU run minus the NVLink
+    transfers (tests/test_tp_multi_gpu.py covers those on >= 2 GPUs).  Checked against the oracle with the same
+    rounding points and against the unsplit engine (one bf16 rounding per partial apart)."""
     ocfg = O.PRESETS[name]
     w = O.init_weights(ocfg, seed=0)
     wave, ns = golden_inputs()
@@ -358,13 +359,16 @@ def test_tensor_parallel_slicing_emulated_on_one_gpu(device, name, world):
     tp.load_state_dict(w)
     r1 = tp.forward(wave.to(device), ns, normalised=True, return_hidden=True)
     for b, nf in enumerate(r0.n_frames):
-        assert rel_err(r1.hidden[b, :nf], r0.hidden[b, :nf]) < 5e-3    # bf16 rounding chains, different fp32 sum order
+        assert rel_err(r1.hidden[b, :nf], r0.hidden[b, :nf]) < 8e-3    # one more bf16 rounding per partial sum
     same = float(np.mean([np.mean(r1.frame_ids[b, :nf] == r0.frame_ids[b, :nf]) for b, nf in enumerate(r0.n_frames)]))
     print(f"tp emulate {name} x{world}: frame-id agreement with the unsplit engine {same:.4f}")
-    assert same >= 0.97
-    emu = O.forward(w, wave, ns, ocfg, emulate_bf16=True, return_logits=True)
+    assert same >= 0.95
+    # the oracle with the tensor-parallel rounding points: every shard's partial sum rounded to bf16, added in rank order
+    emu = O.forward(w, wave, ns, ocfg, emulate_bf16=True, return_logits=True, tp_world=world)
     _, a_m, _ = agreement(r1.frame_ids, emu, NEAR_TIE)
     assert a_m == 1.0
+    for b, nf in enumerate(emu.n_frames):
+        assert rel_err(r1.hidden[b, :nf], emu.hidden[b, :nf]) < 8e-3
     tp.close()
 
 
@@ -460,7 +464,7 @@ def test_one_pipeline_shared_by_four_threads(device):
     assert not errs, errs
     assert got == want
     st = pipe.pool.stats
-    n_win = sum(len(c) // 16000 + 1 for c in clips) * 6
+    n_win = sum(-(-len(c) // 16000) for c in clips) * 6
     assert st["windows"] - base["windows"] == n_win
     print(f"four callers: {st['batches'] - base['batches']} batches for {n_win} windows, "
           f"{st['mixed_batches'] - base['mixed_batches']} of them shared by several callers")

@@ -10,13 +10,17 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-@pytest.mark.parametrize("world,mode", [(2, "nccl"), (2, "fused")])
-def test_tp_matches_single_gpu(world, mode):
+@pytest.mark.parametrize("world,mode,reps", [(2, "nccl", 1), (2, "fused", 1), (2, "fused", 3), (4, "fused", 3),
+                                             (8, "fused", 3)])
+def test_tp_matches_oracle_and_single_gpu(world, mode, reps):
+    """reps = 1: one fused peer-memory kernel per reduction (three windows); reps = 3: nine ragged windows, the
+    half-batch pipeline with the transfers on the copy engines.  Both against the oracle's tensor-parallel rounding
+    points and the unsplit engine (scripts/tp_check.py)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                         "--master-addr", "127.0.0.1", "--master-port", "29731", str(ROOT / "scripts" / "tp_check.py"),
-                        "wide2l", mode],
+                        "wide2l", mode, str(reps)],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "TP OK" in r.stdout
