@@ -97,6 +97,7 @@ class EnginePool:
         self._cv = threading.Condition()
         self._queue: Deque[Tuple[_Request, int]] = collections.deque()
         self._stop = False
+        self._inflight = [0] * len(self.engines)      # batches each engine has in flight (guarded by _cv)
         # what the tests and the stress script read: batches submitted, windows in them, batches that held windows of
         # more than one caller, batches per engine
         self.stats = {"batches": 0, "windows": 0, "mixed_batches": 0, "per_engine": [0] * len(self.engines)}
@@ -150,9 +151,11 @@ class EnginePool:
                 t.join(timeout=30)
 
     # ------------------------------------------------------------------ worker side
-    def _take(self, block: bool) -> List[Tuple[_Request, int]]:
-        """Up to batch_windows jobs of one sample type, whoever queued them.  With several
-        engines the tail of the queue is divided between them instead of going to the first to ask."""
+    def _take(self, k: int, block: bool) -> List[Tuple[_Request, int]]:
+        """Up to batch_windows jobs of one sample type, whoever queued them, for engine k.  With several engines a
+        short queue is divided between them instead of going to the first to ask: an engine takes its share of what is
+        pending, counted over the engines that have nothing in flight (120 windows and 8 idle GPUs: 15 each), or over
+        all engines once everyone is busy (the tail of a long recording)."""
         with self._cv:
             while True:
                 while self._queue and self._queue[0][0].error is not None:   # its caller has been told already
@@ -162,7 +165,9 @@ class EnginePool:
                 self._cv.wait()
             if not self._queue:
                 return []
-            share = -(-len(self._queue) // len(self.engines))              # ceil(pending / engines)
+            idle = sum(1 for j, c in enumerate(self._inflight) if c == 0)
+            over = idle if (idle > 0 and self._inflight[k] == 0) else len(self.engines)
+            share = -(-len(self._queue) // over)                            # ceil(pending / engines to feed)
             limit = max(1, min(self.batch_windows, share))
             dtype = self._queue[0][0].dtype
             taken: List[Tuple[_Request, int]] = []
@@ -180,6 +185,8 @@ class EnginePool:
                     if len(skipped) >= 4 * self.batch_windows:
                         break
             self._queue.extendleft(reversed(skipped))
+            if taken:
+                self._inflight[k] += 1     # counted from the take on, so that the next idle engine sees one fewer idle
             return taken
 
     def _deliver(self, engine: Any, jobs: List[Tuple[_Request, int]], st: _Staging, T: int) -> None:
@@ -217,7 +224,7 @@ class EnginePool:
         inflight: Deque[Tuple[int, List[Tuple[_Request, int]], int, int]] = collections.deque()   # ticket, jobs, slot, T
         n_sub = 0
         while True:
-            jobs = self._take(block=not inflight)
+            jobs = self._take(k, block=not inflight)
             if not jobs and not inflight:
                 if self._stop:
                     return
@@ -256,6 +263,8 @@ class EnginePool:
                         if len({id(req) for req, _ in jobs}) > 1:
                             self.stats["mixed_batches"] += 1
                 except BaseException as e:  # noqa: BLE001 - the callers get the failure, the worker lives on
+                    with self._cv:
+                        self._inflight[k] -= 1
                     self._fail(jobs, e)
             if inflight and (len(inflight) >= self.SLOTS or not jobs):
                 ticket, done_jobs, slot, T = inflight.popleft()
@@ -264,3 +273,5 @@ class EnginePool:
                     self._deliver(engine, done_jobs, slots[slot], T)
                 except BaseException as e:  # noqa: BLE001
                     self._fail(done_jobs, e)
+                with self._cv:
+                    self._inflight[k] -= 1
