@@ -1,14 +1,19 @@
-// Bidirectional self-attention on tcgen05, seventh version (a15), head_dim <= 80 (300M, 1B): attention_v6's pipeline
-// (three query tiles of 128 per CTA, 48-key blocks, one MMA-issuing warp per tile) as a PERSISTENT kernel.  v6 runs one
-// CTA per (query triple, head, window): 2048 CTAs for a 1B step, each paying ~10 k cycles of its ~63 k for the
-// barrier/TMEM set-up, the Q and first K/V loads with nothing to overlap them, the tile stagger and the epilogue.
-// Here one CTA per SM walks a static list of work items; the K/V ring, the barrier phases and the tile stagger run on
-// across items, so the producer fetches the next item's Q and K/V while the tiles finish the current one, and a
-// tile's epilogue overlaps the other tiles' exponentials.
+// Bidirectional self-attention on tcgen05, seventh version (a15), head_dim <= 80 (300M, 1B): a PERSISTENT kernel, one
+// CTA per SM walking a static list of (query group, head, window) work items; NT query tiles of 128 rows per CTA, one
+// MMA-issuing warp per tile, the K/V ring, the barrier phases and the tile stagger running on across items.
 //
-// TMEM columns: S_A S_B S_C (48 each) | P_A P_B P_C (24 used of 32 each) | O_A O_B O_C (head_dim each).
-// Warps: 0-3 / 4-7 / 8-11 softmax + epilogue of tiles A / B / C (warp w owns TMEM lanes [32(w%4), +32)),
-// 12 TMA producer, 13 / 14 / 15 MMA issuers of tiles A / B / C (13 also allocates TMEM).
+// Three shapes are instantiated <NT query tiles, BKV keys per block, SST S buffers per tile> (OASR_ATT_CFG):
+//   3,48,1  round 1's shape: S single-buffered, so S(j+1) can only be issued when the softmax warps have read S(j), and
+//           the P buffer is known to be free through s_full(j+1).  The softmax warps' loop therefore carries the
+//           issuer's round trip (s_free -> wake -> 5 MMAs -> tensor pipe -> s_full, ~700 cycles) beside their
+//           exponentials: measured period ~1650 cycles per 48-key block against a MUFU floor of 1152.
+//   2,64,2  S DOUBLE-buffered (TMEM: 2 x 2 x 64 S + 2 x 32 P + 2 x 80 O = 480 columns): S(j+2) is issued right after
+//           P.V(j), a whole block ahead of its use, so the softmax loop only ever waits for barriers that completed long
+//           ago; 64-key blocks halve the per-key share of the fixed hand-off cost; 352 threads leave 168 registers each.
+//   3,32,2  the same with three tiles and 32-key blocks (480 columns as well).
+// TMEM columns: S[tile][stage] (BKV each) | P[tile] (BKV/2 used, rounded to 16) | O[tile] (head_dim each).
+// Warps: 4 per tile softmax + epilogue (warp w owns TMEM lanes [32(w%4), +32)), then the TMA producer, then one MMA
+// issuer per tile (the first also allocates TMEM).
 #include "host_util.h"
 #include "kernels.cuh"
 #include "attention_common.cuh"
@@ -23,15 +28,12 @@ namespace {
 
 using namespace att;
 
-constexpr int NT = 3;                       // query tiles per CTA
-constexpr int ATT_THREADS = (NT * 4 + 1 + NT) * 32;
 constexpr int BQ = 128;
+__host__ __device__ constexpr int att_threads(int nt) { return (nt * 4 + 1 + nt) * 32; }
 constexpr int MAX_KV_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int KV_PREFETCH = 4;             // K/V blocks of the next work item requested before its Q
 constexpr int START_OFFSET_CYCLES = 450;   // tile X issues its first S this many cycles after tile X-1
-
-__host__ __device__ constexpr int att_bkv(int) { return 48; }
 
 struct Attn7Params {
   int n_qt, n_items;   // query triples per (head, window); work items = n_qt * H * B
@@ -42,6 +44,7 @@ struct Attn7Params {
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
   int start_offset;   // tile X issues its first S this many cycles after tile X-1 (OASR_ATT6_OFFSET overrides)
+  int relay;          // exponential phases in relay (see the softmax warps): 0 off, n: hand on after n 16-column pieces
 };
 constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
 // Tracing is a compile-time option (-DOASR_ATT_TRACING): even a never-taken stamp costs the softmax warps a branch,
@@ -58,17 +61,19 @@ constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softma
   } while (0)
 #endif
 
-template <int HD>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+// POLY: every POLY-th pair of exponentials on the FMA pipe (0: all on MUFU.EX2)
+template <int HD, int POLY, int NT, int BKV, int SST>
+__global__ void __launch_bounds__(att_threads(NT), 1)
 attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
                     const __grid_constant__ CUtensorMap tmk32, const __grid_constant__ CUtensorMap tmk16,
                     const __grid_constant__ CUtensorMap tmo, const Attn7Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int BKV = att_bkv(HD);
+  static_assert(BKV == 32 || BKV == 48 || BKV == 64, "key block");
+  static_assert(SST == 1 || SST == 2, "S buffers per tile");
   constexpr int PSLOT = round16(BKV / 2);
-  constexpr int TM_S = 0, TM_P = NT * BKV, TM_O = NT * BKV + NT * PSLOT;
+  constexpr int TM_S = 0, TM_P = NT * SST * BKV, TM_O = TM_P + NT * PSLOT;
   static_assert(TM_O + NT * HD <= TMEM_COLS, "TMEM budget");
   constexpr int NQK = qk_nchunks(HD);
   constexpr int VW = v_w(HD);
@@ -79,15 +84,17 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   // Barriers first, at fixed offsets from the aligned base (the ring length is a run-time value: anything placed
   // behind it has an address the compiler re-derives from kernel parameters at every use once registers are short,
   // which put ~100 cycles of dependent latency in front of every barrier operation of the softmax warps).
-  // Per tile X, bars[8 X + k]: k = 0 s_full (S_X(j) is in TMEM), 1 s_free (S_X(j) has been read into registers),
-  // 2 p_full (P_X(j) is in TMEM), 3 o_done (P.V_X(j) has retired: O updated, P buffer free), 4 first_s (tile X has
-  // issued its first S of the work item), 5 q_full (Q_X has landed), 6 q_empty (tile X's last S of the item is done).
+  // Per tile X, bars[TB X + k]: k = 0, 1 s_full[stage] (S_X of a block is in TMEM), 2, 3 s_free[stage] (it has been read
+  // into registers), 4 p_full (P_X(j) is in TMEM), 5 o_done (P.V_X(j) has retired: O updated, P buffer free), 6 first_s
+  // (tile X has issued its first S of the work item), 7 q_full (Q_X has landed), 8 q_empty (tile X's last S of the item
+  // is done).  Block g of a tile (counted across work items) uses S stage g % SST; its barriers' parity is (g / SST) & 1.
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  constexpr int S_FULL = 0, S_FREE = 1, P_FULL = 2, O_DONE = 3, FIRST_S = 4, Q_FULL = 5, Q_EMPTY = 6;
-  uint64_t* kv_full = bars + 8 * NT;              // MAX_KV_STAGES
+  constexpr int TB = 10;
+  constexpr int S_FULL = 0, S_FREE = 2, P_FULL = 4, O_DONE = 5, FIRST_S = 6, Q_FULL = 7, Q_EMPTY = 8;
+  uint64_t* kv_full = bars + TB * NT;             // MAX_KV_STAGES
   uint64_t* kv_empty = kv_full + MAX_KV_STAGES;   // MAX_KV_STAGES
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + MAX_KV_STAGES);
-  static_assert((8 * NT + 2 * MAX_KV_STAGES + 1) * 8 <= 1024, "barrier block");
+  static_assert((TB * NT + 2 * MAX_KV_STAGES + 1) * 8 <= 1024, "barrier block");
   uint8_t* sQ = smem + 1024;              // [NT tiles]
   uint8_t* sKV = sQ + NT * q_tile_bytes;  // [stage][K | V]
   uint8_t* sO = sKV + KS * 2 * kv_tile_bytes;   // [softmax warp][32 rows][HD] bf16: staging of the output TMA stores
@@ -101,19 +108,21 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     tma_prefetch_desc(&tmk16);
     tma_prefetch_desc(&tmo);
     for (int i = 0; i < NT; ++i) {
-      mbar_init(&bars[8 * i + Q_FULL], 1);
-      mbar_init(&bars[8 * i + Q_EMPTY], 1);
+      mbar_init(&bars[TB * i + Q_FULL], 1);
+      mbar_init(&bars[TB * i + Q_EMPTY], 1);
     }
     for (int i = 0; i < MAX_KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], NT);  // one commit per tile's MMA issuer
     }
     for (int i = 0; i < NT; ++i) {
-      mbar_init(&bars[8 * i + S_FULL], 1);
-      mbar_init(&bars[8 * i + S_FREE], 4);
-      mbar_init(&bars[8 * i + P_FULL], 4);
-      mbar_init(&bars[8 * i + O_DONE], 1);
-      mbar_init(&bars[8 * i + FIRST_S], 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bars[TB * i + S_FULL + b], 1);
+        mbar_init(&bars[TB * i + S_FREE + b], 4);
+      }
+      mbar_init(&bars[TB * i + P_FULL], 4);
+      mbar_init(&bars[TB * i + O_DONE], 1);
+      mbar_init(&bars[TB * i + FIRST_S], 1);
     }
     fence_barrier_init();
   }
@@ -176,11 +185,11 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         ATT_TRACE(4, it * 8 + 1);
 #pragma unroll
         for (int X = 0; X < NT; ++X) {
-          if (it > 0) mbar_wait(&bars[8 * X + Q_EMPTY], (it - 1) & 1);   // tile X's S MMAs of the previous item have read Q_X
-          mbar_arrive_expect_tx(&bars[8 * X + Q_FULL], q_tile_bytes);
+          if (it > 0) mbar_wait(&bars[TB * X + Q_EMPTY], (it - 1) & 1);   // tile X's S MMAs of the previous item have read Q_X
+          mbar_arrive_expect_tx(&bars[TB * X + Q_FULL], q_tile_bytes);
 #pragma unroll
           for (int c = 0; c < NQK; ++c)
-            tma_load_3d(sQ + X * q_tile_bytes + 2 * BQ * qk_col(HD, c), qmap(qk_w(HD, c)), &bars[8 * X + Q_FULL],
+            tma_load_3d(sQ + X * q_tile_bytes + 2 * BQ * qk_col(HD, c), qmap(qk_w(HD, c)), &bars[TB * X + Q_FULL],
                         qcol + qk_col(HD, c), q0 + X * BQ, b);
           ATT_TRACE(4, it * 8 + 2 + X);
         }
@@ -222,10 +231,10 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
     const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
-    auto issue_s = [&](int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
+    auto issue_s = [&](int st, uint32_t g) {   // S_X(block g) = Q_X K^T for the K tile in stage st: HD/16 MMAs
       const uint32_t q_lo = sq_lo + X * (q_tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
       const uint32_t k_lo = skv_lo + st * (2 * kv_tile_bytes >> 4) + (1u << 16);
-      const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
+      const uint32_t d_tmem = tmem_base + TM_S + (X * SST + (g % SST)) * BKV;
       bool first = true;
 #pragma unroll
       for (int c = 0; c < NQK; ++c) {
@@ -241,7 +250,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
           }
         }
       }
-      if (issuer) umma_commit(&bars[8 * X + S_FULL]);
+      if (issuer) umma_commit(&bars[TB * X + S_FULL + (g % SST)]);
     };
     // O_X += P_X V for the V tile in stage st.  V is MN-major: kv rows of 2*VW bytes, 8-row groups SBO = 16*VW
     // apart, the NV column chunks LBO = 2*BKV*VW apart.
@@ -254,77 +263,95 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       for (int kk = 0; kk < BKV / 16; ++kk)
         if (issuer)
           umma_ts(d_tmem, p_tmem + kk * 8, desc64(hi, v_lo + ((kk * 32 * VW) >> 4)), idesc_o, (j | kk) != 0 ? 1u : 0u);
-      if (issuer) umma_commit(&bars[8 * X + O_DONE]);
+      if (issuer) umma_commit(&bars[TB * X + O_DONE]);
     };
-    int st = 0;            // K/V stage of the block whose P.V comes next
-    uint32_t ph = 0;       // kv_full parity of that stage
+    // Two cursors walk the K/V ring, one block per step and across work items like the producer's: the stage whose
+    // K the next S reads (s_*) and the stage whose V the next P.V reads (pv_*); the S cursor runs SST blocks ahead.
+    int s_st = 0, pv_st = 0;
+    uint32_t s_ph = 0;
     uint32_t it = 0, gb = 0;   // items / key blocks of this tile finished so far (barrier phases run on across items)
+    // S of block b of the current item (global block g = gb + b).  Waits for its K tile and for the softmax warps to
+    // have read the previous block that used the same S stage (g - SST; the first blocks of an item: the last ones of
+    // the previous item).
+    auto next_s = [&](int b, int nblk) {
+      const uint32_t g = gb + b;
+      mbar_wait(&kv_full[s_st], s_ph);
+      if (g >= (uint32_t)SST) mbar_wait(&bars[TB * X + S_FREE + (g % SST)], ((g / SST) - 1) & 1);
+      tc_fence_after();
+      issue_s(s_st, g);
+      if (b + 1 == nblk && issuer) umma_commit(&bars[TB * X + Q_EMPTY]);   // this tile's last S of the item has been issued
+      if (++s_st == KS) {
+        s_st = 0;
+        s_ph ^= 1;
+      }
+    };
     for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
       int q0, h, b, n_keys;
       item(w, q0, h, b, n_keys);
       const int nblk = (n_keys + BKV - 1) / BKV;
       if (nblk == 0) continue;
-      mbar_wait(&bars[8 * X + Q_FULL], it & 1);
+      mbar_wait(&bars[TB * X + Q_FULL], it & 1);
       if (lane == 0 && X == 0) ATT_TRACE(4, 128 + it * 4);
-      mbar_wait(&kv_full[st], ph);
+      mbar_wait(&kv_full[s_st], s_ph);
       if (lane == 0 && X == 0) ATT_TRACE(4, 128 + it * 4 + 1);
       if (X > 0) {
-        // Every item starts the tiles a fraction of a block period apart, in the order A, B, C: the ~430 cycles a
-        // softmax warp spends outside its exponentials per block (P hand-off, TMEM loads) then fall into the
-        // exponential phases of the other two tiles.  The distance drifts over an item; this brings it back.
-        mbar_wait(&bars[8 * (X - 1) + FIRST_S], it & 1);
+        // Every item starts the tiles a fraction of a block period apart, in the order A, B, C: the cycles a softmax
+        // warp spends outside its exponentials per block (P hand-off, TMEM loads) then fall into the exponential
+        // phases of the other tiles.  The distance drifts over an item; this brings it back.
+        mbar_wait(&bars[TB * (X - 1) + FIRST_S], it & 1);
         const long long t_start = clock64();
         while (clock64() - t_start < (long long)p.start_offset) {
         }
       }
-      if (it > 0) mbar_wait(&bars[8 * X + S_FREE], (gb - 1) & 1);   // the last S of the previous item has been read
-      tc_fence_after();
-      issue_s(st);
-      if (issuer) mbar_arrive(&bars[8 * X + FIRST_S]);
+      next_s(0, nblk);
+      if (issuer) mbar_arrive(&bars[TB * X + FIRST_S]);
       if (lane == 0 && X == 0 && gb > 0) ATT_TRACE(0, (gb - 1) * 2);
-      if (nblk == 1 && issuer) umma_commit(&bars[8 * X + Q_EMPTY]);
-      int st_next = st + 1 == KS ? 0 : st + 1;
-      uint32_t ph_next = st + 1 == KS ? ph ^ 1 : ph;
+      if (SST == 2 && nblk > 1) next_s(1, nblk);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          mbar_wait(&kv_full[st_next], ph_next);
-          mbar_wait(&bars[8 * X + S_FREE], (gb + j) & 1);
-          tc_fence_after();
-          issue_s(st_next);
-          if (j + 2 == nblk && issuer) umma_commit(&bars[8 * X + Q_EMPTY]);   // this tile's last S of the item has been issued
+        // one S buffer: S(j+1) has to go out BEFORE this thread blocks on P(j), or the softmax warps would find no
+        // scores after their hand-off; two buffers: S(j+1) is out already and S(j+2) follows P.V(j)
+        if (SST == 1 && j + 1 < nblk) {
+          next_s(j + 1, nblk);
           if (lane == 0 && X == 0) ATT_TRACE(0, (gb + j) * 2);
         }
-        mbar_wait(&bars[8 * X + P_FULL], (gb + j) & 1);
+        mbar_wait(&bars[TB * X + P_FULL], (gb + j) & 1);
         tc_fence_after();
-        issue_pv(st, j);
+        issue_pv(pv_st, j);
         if (lane == 0 && X == 0) ATT_TRACE(0, (gb + j) * 2 + 1);
-        if (issuer) umma_commit(&kv_empty[st]);   // K/V of block j: this tile's MMAs reading them have been issued
+        if (issuer) umma_commit(&kv_empty[pv_st]);   // K/V of block j: this tile's MMAs reading them have been issued
         __syncwarp();
-        st = st_next;
-        ph = ph_next;
-        if (++st_next == KS) {
-          st_next = 0;
-          ph_next ^= 1;
-        }
+        if (++pv_st == KS) pv_st = 0;
+        if (SST == 2 && j + 2 < nblk) next_s(j + 2, nblk);
       }
       gb += nblk;
       ++it;
     }
   } else {
-    // ---------------------------------------------------------------- softmax + epilogue (warps 0-11)
+    // ---------------------------------------------------------------- softmax + epilogue (warps 0 .. 4 NT - 1)
     const int X = warp >> 2;                     // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;        // row within the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t t_s = t_lane + TM_S + X * BKV;
+    const uint32_t t_s0 = t_lane + TM_S + X * SST * BKV;   // S stage b of this tile: + b * BKV
     const uint32_t t_p = t_lane + TM_P + X * PSLOT;
+    constexpr int VB = BKV - 32;                           // columns beyond the first 32-column chunk: 0, 16 or 32
     const float c = p.scale_log2e;
     RowState<HD> rs;
     rs.t_o = t_lane + TM_O + X * HD;
-    rs.o_done = &bars[8 * X + O_DONE];
-    auto signal_s_free = [&]() {
+    rs.o_done = &bars[TB * X + O_DONE];
+    auto signal_s_free = [&](uint32_t g) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[8 * X + S_FREE]);
+      if (lane == 0) mbar_arrive(&bars[TB * X + S_FREE + (g % SST)]);
+    };
+    uint32_t va[32], vb[VB > 0 ? VB : 1];
+    // waits for S of block g (counted across items) and requests it from TMEM into va / vb
+    auto request_s = [&](uint32_t g) {
+      mbar_wait(&bars[TB * X + S_FULL + (g % SST)], (g / SST) & 1);
+      tc_fence_after();
+      const uint32_t t_s = t_s0 + (g % SST) * BKV;
+      tmem_ld32(t_s, va);
+      if constexpr (VB == 16) tmem_ld16(t_s + 32, reinterpret_cast<uint32_t(&)[16]>(vb));
+      if constexpr (VB == 32) tmem_ld32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(vb));
     };
     uint32_t gb = 0;
     for (int w = blockIdx.x; w < p.n_items; w += gridDim.x) {
@@ -349,13 +376,9 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       rs.m_ref = 0.f;
       rs.sum = 0.f;
       rs.gb = gb;
-      uint32_t va[32], vb[16];
       if (warp == 0 && lane == 0) ATT_TRACE(4, 192 + (gb / 32) * 8 + 2);
-      mbar_wait(&bars[8 * X + S_FULL], gb & 1);
-      tc_fence_after();
+      request_s(gb);
       if (warp == 0 && lane == 0) ATT_TRACE(4, 192 + (gb / 32) * 8 + 3);
-      tmem_ld32(t_s, va);
-      tmem_ld16(t_s + 32, vb);
       for (int j = 0; j < nblk; ++j) {
         const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
         rs.j = j;
@@ -364,42 +387,59 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         uint32_t pk[BKV / 2];
         const bool tr = (warp & 3) == 0 && lane == 0;
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6);
-        // va / vb: columns [0,32) / [32,48) of S(j), requested at the end of the previous iteration: S goes back to
+        // va / vb: columns [0,32) / [32,BKV) of S(j), requested at the end of the previous iteration: S goes back to
         // the MMA warp before the first exponential
         tmem_ld_wait_on(va);
-        tmem_ld_wait_on16(vb);
-        signal_s_free();
+        if constexpr (VB == 16) tmem_ld_wait_on16(reinterpret_cast<uint32_t(&)[16]>(vb));
+        if constexpr (VB == 32) tmem_ld_wait_on(reinterpret_cast<uint32_t(&)[32]>(vb));
+        signal_s_free(gb + j);
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 1);
-        static_assert(BKV == 48, "key block");
+        // Exponential phases in RELAY.  Left alone, the NT softmax warps that share an SM sub-partition fall into
+        // lock-step: they queue at the MUFU pipe together (24 cycles per column for three warps, the pipe's limit) and
+        // then leave it idle together for the ~600 cycles each spends on its hand-off (TMEM store, barrier round trips)
+        // - the timeline showed period = exponentials at the shared rate + hand-off, 2030 cycles per 48-key block
+        // against a MUFU floor of 1152 (profiles/r2_notes.md).  The relay keeps them apart: tile X may start the
+        // exponentials of its block g only when tile X-1 (tile NT-1's block g-1 for tile 0) is `relay` 16-column
+        // pieces into its own, so that one tile's hand-off falls into the others' exponentials.  Hardware named
+        // barriers 1 + X (arrive by the 128 threads of tile X, sync by the 128 of its successor): a few cycles each.
+        // No tile can run two blocks ahead of its successor (its next start waits, around the ring, for the
+        // successor's start), so a barrier generation never receives arrivals of two blocks.
+        const uint32_t g_blk = gb + j;
+        if (p.relay > 0 && (X > 0 || g_blk > 0)) named_bar_sync(1 + (X + NT - 1) % NT, 256);
         if (ncols == BKV) {
-          softmax_chunk<HD, 0, 32, false>(va, ncols, c, rs, pk);
+          softmax_chunk<HD, 0, 16, false, BKV / 2, POLY>(va, ncols, c, rs, pk);
+          if (p.relay == 1) named_bar_arrive(1 + X, 256);
+          softmax_chunk<HD, 16, 16, false, BKV / 2, POLY>(va + 16, ncols, c, rs, pk);
+          if (p.relay >= 2) named_bar_arrive(1 + X, 256);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          softmax_chunk<HD, 32, 16, false>(vb, ncols, c, rs, pk);
+          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, false, BKV / 2, POLY>(vb, ncols, c, rs, pk);
         } else {
-          softmax_chunk<HD, 0, 32, true>(va, ncols, c, rs, pk);
+          softmax_chunk<HD, 0, 16, true, BKV / 2, POLY>(va, ncols, c, rs, pk);
+          if (p.relay == 1) named_bar_arrive(1 + X, 256);
+          softmax_chunk<HD, 16, 16, true, BKV / 2, POLY>(va + 16, ncols, c, rs, pk);
+          if (p.relay >= 2) named_bar_arrive(1 + X, 256);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          softmax_chunk<HD, 32, 16, true>(vb, ncols, c, rs, pk);
+          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, true, BKV / 2, POLY>(vb, ncols, c, rs, pk);
         }
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 4);
-        // S(j+1) was issued when s_free(j) arrived, i.e. long ago: request its first two chunks now so that the TMEM
-        // read latency hides under the P hand-off below
+        // One S buffer: S(j+1) was issued when s_free(j) arrived.  Two: it was issued a whole block ago.  Either way
+        // its chunks are requested now so that the TMEM read latency hides under the P hand-off below.
         if (j + 1 < nblk) {
-          mbar_wait(&bars[8 * X + S_FULL], (gb + j + 1) & 1);
+          request_s(gb + j + 1);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 3);
-          tc_fence_after();
-          tmem_ld32(t_s, va);
-          tmem_ld16(t_s + 32, vb);
         }
         {
           const float2 t = fadd2(rs.sm[0], rs.sm[1]);
           rs.sum += t.x + t.y;
         }
-        // The P buffer is free once P.V_X(j-1) has retired.  S_X(j+1) was issued after P.V_X(j-1) by the same thread
-        // and tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it; only the
-        // last block has to ask o_done (an mbarrier round trip costs ~150 cycles on this critical path).  Block 0 of
-        // a later item: the epilogue below has waited for the previous item's last P.V.
-        if (j > 0 && j + 1 >= nblk) {
-          mbar_wait(&bars[8 * X + O_DONE], (gb + j - 1) & 1);
+        // The P buffer is free once P.V_X(j-1) has retired.  One S buffer: S_X(j+1) was issued after P.V_X(j-1) by the
+        // same thread and tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it and
+        // only the last block has to ask o_done (an mbarrier round trip costs ~100 cycles on this critical path).  Two S
+        // buffers: S_X(j+1) went out BEFORE P.V_X(j-1), so o_done is asked every time - P.V_X(j-1) was issued one
+        // exponential phase ago and has normally retired.  Block 0 of a later item: the epilogue below has waited for
+        // the previous item's last P.V.
+        if (j > 0 && (SST == 2 || j + 1 >= nblk)) {
+          mbar_wait(&bars[TB * X + O_DONE], (gb + j - 1) & 1);
           tc_fence_after();
         }
 #pragma unroll
@@ -418,11 +458,11 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[8 * X + P_FULL]);
+        if (lane == 0) mbar_arrive(&bars[TB * X + P_FULL]);
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 5);
       }
       // epilogue: O / rowsum -> bf16
-      mbar_wait(&bars[8 * X + O_DONE], (gb + nblk - 1) & 1);
+      mbar_wait(&bars[TB * X + O_DONE], (gb + nblk - 1) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) ATT_TRACE(4, 192 + (gb / 32) * 8);
       const float inv = 1.0f / rs.sum;
@@ -498,7 +538,15 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "attention: buffers must be 16-byte aligned");
   const int d = H * hd;
-  const int bkv = att_bkv(hd);
+  // OASR_ATT_CFG = <tiles><keys per block> of the instantiated shapes: 348 (three tiles, 48-key blocks, one S buffer:
+  // round 1's shape), 264 (two tiles, 64-key blocks, two S buffers) or 332 (three tiles, 32-key blocks, two S
+  // buffers; tests/test_gpu_kernels.py::test_attention_shapes_agree).
+  static const int cfg_env = [] {
+    const char* e = std::getenv("OASR_ATT_CFG");
+    return e != nullptr ? std::atoi(e) : 348;
+  }();
+  const int cfg = (cfg_env == 348 || cfg_env == 264 || cfg_env == 332) ? cfg_env : 348;
+  const int NT = cfg / 100, bkv = cfg % 100;
   AttMaps m;
   {
     std::lock_guard<std::mutex> g(g_att7_mu);
@@ -529,7 +577,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   }
   Attn7Params p;
   const int q_tile_bytes = BQ * hd * 2, kv_tile_bytes = bkv * hd * 2;
-  int kv_stages = (227 * 1024 - 2048 - 2 * NT * q_tile_bytes) / (2 * kv_tile_bytes);
+  int kv_stages = (227 * 1024 - 2048 - 2 * NT * q_tile_bytes) / (2 * kv_tile_bytes);   // Q tiles + output staging of the same size
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
   OASR_REQUIRE(kv_stages >= 3, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
@@ -546,6 +594,11 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
     return e != nullptr ? std::atoi(e) : START_OFFSET_CYCLES;
   }();
   p.start_offset = start_offset;
+  static const int relay = [] {
+    const char* e = std::getenv("OASR_ATT_RELAY");   // 0: free-running tiles; 1 / 2: hand on after 16 / 32 columns
+    return e != nullptr ? std::atoi(e) : 1;
+  }();
+  p.relay = relay < 0 ? 0 : (relay > 2 ? 2 : relay);
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
   if (trace_path != nullptr) {
     OASR_CUDA_CHECK(cudaMalloc(&p.trace, 5 * TRACE_EVENTS * sizeof(long long)));
@@ -562,18 +615,32 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   const int want = grid_override > 0 ? grid_override : num_sms;
   dim3 grid(p.n_items < want ? p.n_items : want);
   cudaError_t attr_err = cudaSuccess;
-#define OASR_ATT_CASE(HDV)                                                                                      \
-  case HDV: {                                                                                                   \
-    static unsigned long long attr_mask = 0;                                                                    \
-    if (first_use_on_this_device(&attr_mask)) {                                                                 \
-      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      227 * 1024);                                                              \
-    }                                                                                                           \
-    if (attr_err == cudaSuccess)                                                                                \
-      attention_v7_kernel<HDV><<<grid, ATT_THREADS, smem_bytes, stream>>>(m.tm[0], m.tm[1], m.tm[2], m.tm[3], \
-                                                                             m.tm[4], m.tm[5], m.tm[6], p);              \
-    break;                                                                                                      \
+  // OASR_ATT_POLY = 3: every third pair of exponentials on the FMA pipe (default 0: all on MUFU.EX2; measured slower
+  // in every shape so far, profiles/r2_notes.md; tests/test_gpu_kernels.py::test_attention_poly_settings_agree)
+  static const int poly_env = [] {
+    const char* e = std::getenv("OASR_ATT_POLY");
+    return e != nullptr ? std::atoi(e) : 0;
+  }();
+  const int poly = poly_env == 3 ? 3 : 0;
+#define OASR_ATT_LAUNCH(HDV, PV, NTV, BKVV, SSTV)                                                                      \
+  {                                                                                                                    \
+    static unsigned long long attr_mask = 0;                                                                           \
+    if (first_use_on_this_device(&attr_mask))                                                                          \
+      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV, PV, NTV, BKVV, SSTV>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                        \
+    if (attr_err == cudaSuccess)                                                                                       \
+      attention_v7_kernel<HDV, PV, NTV, BKVV, SSTV><<<grid, att_threads(NTV), smem_bytes, stream>>>(                   \
+          m.tm[0], m.tm[1], m.tm[2], m.tm[3], m.tm[4], m.tm[5], m.tm[6], p);                                           \
   }
+#define OASR_ATT_SHAPES(HDV, PV)                                  \
+  if (cfg == 264) OASR_ATT_LAUNCH(HDV, PV, 2, 64, 2)              \
+  else if (cfg == 332) OASR_ATT_LAUNCH(HDV, PV, 3, 32, 2)         \
+  else OASR_ATT_LAUNCH(HDV, PV, 3, 48, 1)
+#define OASR_ATT_CASE(HDV)                       \
+  case HDV:                                      \
+    if (poly == 3) { OASR_ATT_SHAPES(HDV, 3) }   \
+    else { OASR_ATT_SHAPES(HDV, 0) }             \
+    break;
   switch (hd) {
     OASR_ATT_CASE(16)
     OASR_ATT_CASE(32)
@@ -583,6 +650,8 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
     default: return fail(OASR_ERR_UNSUPPORTED, "attention v7: head_dim must be a multiple of 16 in [16, 80]");
   }
 #undef OASR_ATT_CASE
+#undef OASR_ATT_SHAPES
+#undef OASR_ATT_LAUNCH
   OASR_CUDA_CHECK(attr_err);
   OASR_CUDA_CHECK(cudaGetLastError());
   if (p.trace != nullptr) {

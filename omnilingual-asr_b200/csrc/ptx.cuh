@@ -534,5 +534,9 @@ __device__ __forceinline__ void gelu_erf_x2(f32x2 x, float& y0, float& y1) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// counts the warp's threads into barrier `id` without waiting (the other side waits with named_bar_sync)
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 }  // namespace oasr

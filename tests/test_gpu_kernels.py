@@ -311,6 +311,56 @@ def test_ctc_collapse_kats_and_random(device):
     assert (of.cpu().numpy() == want_pos).all()
 
 
+def _attention_variant(tmp_path, env, B, T, H, hd):
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    out = tmp_path / ("att_" + "_".join(f"{k}{v}" for k, v in env.items()) + f"_{hd}.npy")
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, str(root / "scripts" / "attention_variant.py"), str(out), str(B), str(T), str(H), str(hd)],
+                       env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.load(out)
+
+
+@pytest.mark.parametrize("hd", [64, 80])
+def test_attention_poly_settings_agree(device, tmp_path, hd):
+    """OASR_ATT_POLY=3 (every third pair of exponentials evaluated by the FMA-pipe polynomial instead of MUFU.EX2;
+    default 0): same attention output up to rare one-ulp flips of a bf16 rounding (the polynomial is accurate to
+    2.6e-6, 1/750 of a bf16 half-ulp)."""
+    ref = _attention_variant(tmp_path, {"OASR_ATT_POLY": "0"}, 2, 700, 4, hd)
+    for poly in ("3",):
+        got = _attention_variant(tmp_path, {"OASR_ATT_POLY": poly}, 2, 700, 4, hd)
+        same = float((got == ref).mean())
+        worst = float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-9))
+        print(f"hd {hd} OASR_ATT_POLY={poly}: {same:.5f} of the outputs identical to the all-MUFU kernel, max diff {worst:.2e} of max |o|")
+        assert same > 0.998 and worst < 1e-2
+
+
+@pytest.mark.parametrize("hd", [32, 64, 80])
+def test_attention_shapes_agree(device, tmp_path, hd):
+    """OASR_ATT_CFG: the three instantiated shapes of the persistent kernel (tiles x keys per block x S buffers: 264
+    default, 348 round 1's, 332) compute the same attention - ragged windows, several work items per CTA, the
+    reference-move path not excluded - up to fp32 summation order in P.V (different key-block boundaries)."""
+    outs = {cfg: _attention_variant(tmp_path, {"OASR_ATT_CFG": cfg}, 3, 700, 4, hd) for cfg in ("264", "348", "332")}
+    ref = outs["348"]
+    for cfg in ("264", "332"):
+        same = float((outs[cfg] == ref).mean())
+        worst = float(np.abs(outs[cfg] - ref).max() / max(np.abs(ref).max(), 1e-9))
+        print(f"hd {hd} OASR_ATT_CFG={cfg}: {same:.5f} of the outputs identical to 348, max diff {worst:.2e} of max |o|")
+        assert same > 0.99 and worst < 1e-2
+
+
+def test_attention_env_switch_v4(device, tmp_path):
+    """OASR_ATTN=4 forces the two-tile kernel (the default above head_dim 80) at head_dim 80: same result as v7."""
+    a = _attention_variant(tmp_path, {"OASR_ATTN": "7"}, 2, 500, 4, 80)
+    b = _attention_variant(tmp_path, {"OASR_ATTN": "4"}, 2, 500, 4, 80)
+    assert float((a == b).mean()) > 0.995 and float(np.abs(a - b).max()) < 2e-2 * float(np.abs(a).max())
+
+
 # ------------------------------------------------------------------------------------------- exactness
 def test_outputs_bit_identical_to_rounded_reference(device, gen):
     """Each bf16-producing kernel must equal 'fp64 reference rounded once to bf16' on >= 99.5 % of its outputs
