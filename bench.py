@@ -162,8 +162,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_throughput(model: str, windows: int, reps: int = 1, warmup: int = 0):
-    """Times the CPU oracle (PyTorch eager fp32, all host threads) on `windows` 30 s windows."""
+def cpu_oracle_throughput(model: str, windows: int, reps: int = 1, warmup: int = 0, bf16: bool = False):
+    """Times the CPU oracle (PyTorch eager, all host threads) on `windows` 30 s windows: fp32 (the headline baseline) or,
+    with bf16=True, the same graph under torch.autocast(cpu, bfloat16) - the AMX path BASELINE.md section 3 asks for
+    beside it (contractions in bf16, LayerNorm / softmax in fp32)."""
     from oracle import ctc_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -172,7 +174,9 @@ def cpu_oracle_throughput(model: str, windows: int, reps: int = 1, warmup: int =
     wave = synthetic_windows(windows, 1234)
     ns = [wave.shape[1]] * windows
     times = []
-    with torch.no_grad():
+    import contextlib
+    ctx = torch.autocast("cpu", dtype=torch.bfloat16) if bf16 else contextlib.nullcontext()
+    with torch.no_grad(), ctx:
         for i in range(warmup + reps):
             t0 = time.perf_counter()
             wn = O.wave_layer_norm(wave, ns)
@@ -444,6 +448,12 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{args.cpu_windows} x 30 s windows, one pass, PyTorch eager fp32 oracle "
                                           f"({times[0]:.1f} s)"}
+        try:   # the same oracle with bf16 contractions (AMX where the host has it): reported beside the fp32 baseline
+            v16, _, t16 = cpu_oracle_throughput(args.model, args.cpu_windows, reps=1, warmup=1, bf16=True)
+            line["cpu_baseline"]["bf16_autocast"] = {"value": v16, "unit": UNIT,
+                                                     "sample": f"{args.cpu_windows} x 30 s windows, second of two passes ({t16[0]:.1f} s)"}
+        except Exception as e:  # noqa: BLE001
+            line["cpu_baseline"]["bf16_autocast"] = {"error": str(e)[:200]}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -201,4 +201,72 @@ def build_eaf(data: Mapping[str, Any], date: Optional[str] = None) -> str:
         f"{slots_xml}\n    </TIME_ORDER>\n{transcript_tiers}\n{additional}\n{types}\n</ANNOTATION_DOCUMENT>")
 
 
-__all__ = ["result_dict", "build_srt", "build_textgrid", "build_eaf"]
+def build_eaf_with_words(data: Mapping[str, Any], *, media_url: str = "", relative_media_url: str = "",
+                         date: Optional[str] = None) -> str:
+    """ELAN 3.0 document in the layout of the reference's bundled `gettysburg.eaf` (written by the former LOCAL pipeline,
+    wav2elan: /root/reference/gettysburg.eaf:1-135): a `transcription` tier per speaker plus a time-aligned `word` tier
+    `<speaker>_words`, both carrying PARTICIPANT; annotation and time-slot ids run segment by segment, each segment
+    followed by its words (a1 ts1/ts2, then a2.. for its words, then the next segment); times in integer
+    milliseconds.  Needs `word_timestamps=True` results for the word tier; segments without words get none.
+    tests/test_export.py rebuilds the reference file byte for byte from its own content (tests/golden/gettysburg_eaf.json).
+    """
+    segs = data["segments"]
+    speakers: List[str] = []
+    slots: List[str] = []
+    seg_ann: Dict[str, List[str]] = {}
+    word_ann: Dict[str, List[str]] = {}
+    ts_id = ann_id = 1
+
+    def ms(seg: Any, name: str) -> int:
+        v = _get(seg, name + "_ms")
+        return int(v) if v is not None else _js_round(_get(seg, name) * 1000)
+
+    def annotation(value: str, t0: int, t1: int) -> str:
+        nonlocal ts_id, ann_id
+        a, b = f"ts{ts_id}", f"ts{ts_id + 1}"
+        slots.append(f'    <TIME_SLOT TIME_SLOT_ID="{a}" TIME_VALUE="{t0}"/>')
+        slots.append(f'    <TIME_SLOT TIME_SLOT_ID="{b}" TIME_VALUE="{t1}"/>')
+        xml = ("    <ANNOTATION>\n"
+               f'      <ALIGNABLE_ANNOTATION ANNOTATION_ID="a{ann_id}" TIME_SLOT_REF1="{a}" TIME_SLOT_REF2="{b}">\n'
+               f"        <ANNOTATION_VALUE>{_xml(value)}</ANNOTATION_VALUE>\n"
+               "      </ALIGNABLE_ANNOTATION>\n"
+               "    </ANNOTATION>")
+        ts_id += 2
+        ann_id += 1
+        return xml
+
+    for seg in segs:
+        sp = _get(seg, "speaker")
+        if sp not in speakers:
+            speakers.append(sp)
+            seg_ann[sp] = []
+            word_ann[sp] = []
+        seg_ann[sp].append(annotation(_get(seg, "text"), ms(seg, "start"), ms(seg, "end")))
+        for w in (_get(seg, "words") or []):
+            word_ann[sp].append(annotation(_get(w, "word"), ms(w, "start"), ms(w, "end")))
+    if date is None:
+        date = datetime.now(timezone.utc).strftime("%Y-%m-%dT%H:%M:%SZ")
+    out = ['<?xml version="1.0" encoding="utf-8"?>',
+           f'<ANNOTATION_DOCUMENT xmlns:xsi="http://www.w3.org/2001/XMLSchema-instance" AUTHOR="" DATE="{date}" '
+           'FORMAT="3.0" VERSION="3.0" xsi:noNamespaceSchemaLocation="http://www.mpi.nl/tools/elan/EAFv3.0.xsd">',
+           '  <HEADER MEDIA_FILE="" TIME_UNITS="milliseconds">',
+           f'    <MEDIA_DESCRIPTOR MEDIA_URL="{_xml(media_url)}" MIME_TYPE="audio/wav" '
+           f'RELATIVE_MEDIA_URL="{_xml(relative_media_url)}"/>',
+           "  </HEADER>",
+           '  <LOCALE LANG_ID="und"/>',
+           '  <LINGUISTIC_TYPE LINGUISTIC_TYPE_ID="transcription" TIME_ALIGNABLE="true" GRAPHIC_REFERENCES="false"/>',
+           '  <LINGUISTIC_TYPE LINGUISTIC_TYPE_ID="word" TIME_ALIGNABLE="true" GRAPHIC_REFERENCES="false"/>',
+           "  <TIME_ORDER>"] + slots + ["  </TIME_ORDER>"]
+    for sp in speakers:
+        out.append(f'  <TIER TIER_ID="{_xml(sp)}" LINGUISTIC_TYPE_REF="transcription" PARTICIPANT="{_xml(sp)}">')
+        out += seg_ann[sp]
+        out.append("  </TIER>")
+        if word_ann[sp]:
+            out.append(f'  <TIER TIER_ID="{_xml(sp)}_words" LINGUISTIC_TYPE_REF="word" PARTICIPANT="{_xml(sp)}">')
+            out += word_ann[sp]
+            out.append("  </TIER>")
+    out.append("</ANNOTATION_DOCUMENT>")
+    return "\n".join(out) + "\n"
+
+
+__all__ = ["result_dict", "build_srt", "build_textgrid", "build_eaf", "build_eaf_with_words"]

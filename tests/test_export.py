@@ -62,3 +62,38 @@ def test_eaf_is_wellformed_and_follows_the_tier_rules():
     assert 'MEDIA_URL="a&amp;b&quot;.wav"' in eaf
     types = [t.attrib["LINGUISTIC_TYPE_ID"] for t in root.findall("LINGUISTIC_TYPE")]
     assert types == ["transcription", "language", "translation"]           # hasTranslation is true, the tier is empty
+
+
+def test_eaf_with_words_rebuilds_the_reference_golden_byte_for_byte():
+    """The one reference-held golden of the export layer: /root/reference/gettysburg.eaf (written by the former local
+    pipeline; ELAN 3.0 with a transcription tier and a time-aligned word tier per speaker).  Its CONTENT is committed as
+    tests/golden/gettysburg_eaf.json (tests/golden/make_eaf_fixture.py); build_eaf_with_words must reproduce the FILE -
+    tier / linguistic-type / time-slot layout, id numbering, attribute order, whitespace - checked by sha256."""
+    import hashlib
+    import json
+    from pathlib import Path
+    from omnilingual_asr.export import build_eaf_with_words
+    g = json.loads((Path(__file__).parent / "golden" / "gettysburg_eaf.json").read_text())
+    doc = build_eaf_with_words({"segments": g["segments"]}, media_url=g["media_url"],
+                               relative_media_url=g["relative_media_url"], date=g["date"])
+    assert hashlib.sha256(doc.encode("utf-8")).hexdigest() == g["sha256"]
+    assert doc.count("<TIME_SLOT ") == g["n_time_slots"] == 2 * (len(g["segments"]) + sum(len(s["words"]) for s in g["segments"]))
+
+
+def test_eaf_with_words_from_pipeline_segments():
+    """The same writer on what the pipeline returns (seconds, WordTimestamp objects): integer milliseconds, one word tier
+    per speaker, segments without words contribute none."""
+    import xml.etree.ElementTree as ET
+    from omnilingual_asr.export import build_eaf_with_words
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCTranscriptSegment, WordTimestamp
+    segs = [CTCTranscriptSegment(0.352, 1.0, "Speaker 1", "a <b>", words=[WordTimestamp("a", 0.4, 0.5), WordTimestamp("<b>", 0.6, 0.95)]),
+            CTCTranscriptSegment(2.0, 3.5, "Speaker 1", "c", words=None)]
+    root = ET.fromstring(build_eaf_with_words({"segments": segs}, date="2026-01-01T00:00:00Z"))
+    tiers = {t.attrib["TIER_ID"]: t for t in root.findall("TIER")}
+    assert set(tiers) == {"Speaker 1", "Speaker 1_words"}
+    slots = {t.attrib["TIME_SLOT_ID"]: int(t.attrib["TIME_VALUE"]) for t in root.find("TIME_ORDER")}
+    assert [slots[f"ts{i}"] for i in range(1, 9)] == [352, 1000, 400, 500, 600, 950, 2000, 3500]
+    words = [a.find("ANNOTATION_VALUE").text for a in tiers["Speaker 1_words"].findall("ANNOTATION/ALIGNABLE_ANNOTATION")]
+    assert words == ["a", "<b>"]
+    ids = [a.attrib["ANNOTATION_ID"] for a in tiers["Speaker 1"].findall("ANNOTATION/ALIGNABLE_ANNOTATION")]
+    assert ids == ["a1", "a4"]
