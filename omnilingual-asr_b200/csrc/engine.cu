@@ -188,7 +188,7 @@ struct OasrEngine {
   bool tp_emulated = false;
   void* tp_comm = nullptr;
   float* part = nullptr;            // [M, d] fp32 partial sums of the row-parallel GEMMs (NCCL mode only)
-  __nv_bfloat16* part_bf16 = nullptr;   // peer-memory path: [M, d] bf16 partial sums (in the arena); emulation: [shards][M, d]
+  __nv_bfloat16* part_bf16 = nullptr;   // emulation of the split on one GPU: [shards][M, d] bf16 partial sums
   long long part_shard_stride = 0;  // elements between the shards' partials (emulation)
   unsigned int* tp_err_host = nullptr;   // host-mapped error word the flag waits set on a timeout
   unsigned int* tp_err_dev = nullptr;
@@ -200,13 +200,10 @@ struct OasrEngine {
   TpPeerView tp_view2{};            // second flag set (half-batch 1 in overlap mode)
   unsigned long long tp_epoch2 = 0;
   cudaStream_t tp_comm_stream2 = nullptr;
-  __nv_bfloat16* tp_recv2 = nullptr;
   bool tp_fused = false;
   unsigned long long tp_epoch = 0;
   // overlap mode of the peer-memory path: the reduce kernels run on their own stream beside the other half-batch's GEMMs
   cudaStream_t tp_comm_stream = nullptr;
-  __nv_bfloat16* tp_recv = nullptr; // copy-engine mode: the peers' partial rows of this rank's row share
-  size_t tp_recv_bytes = 0;
   cudaEvent_t tp_ev_compute[2] = {nullptr, nullptr}, tp_ev_reduce[2] = {nullptr, nullptr};
   // shapes of the last forward (debug buffers)
   int last_B = 0, last_L = 0, last_T = 0, last_fe_idx = 0;
@@ -288,7 +285,8 @@ int ensure_workspace(OasrEngine* e, int B, int L) {
   OASR_TRY(A((void**)&e->att, (size_t)M * d * 2, false));
   OASR_TRY(A((void**)&e->ffn, (size_t)M * F * 2, false));
   if (e->tp_arena != nullptr) {
-    e->part_bf16 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(e->tp_arena) + e->tp_off_part);
+    // peer-memory path: the partial sums never sit in a buffer of their producer - the GEMM epilogue routes them into
+    // the owners' receive regions (tp_view.recv, inside the arenas)
   } else if (e->tp_emulated) {
     e->part_shard_stride = M * d;
     OASR_TRY(A((void**)&e->part_bf16, (size_t)e->tp_local * M * d * 2, false));
@@ -381,14 +379,26 @@ int run_posconv(float* x, int B, int T, int d, int groups, int k, int k_pad, con
   return gemm_bf16_tcgen05(a, st);
 }
 
-// Tensor-parallel encoder layers with the reductions' transfers beside compute (peer-memory path, B >= 2).
-// The batch is cut into two half-batches of windows (attention never crosses a window).  All compute kernels stay on
-// the caller's stream, in the order  P1(h0) P1(h1) P2(h0) P2(h1)  per layer (P1 = QKV, attention, out-proj partial;
-// P2 = FFN1, FFN2 partial).  The all-reduce + residual + LayerNorm of a half-batch (tp_dma_reduce_layernorm: NVLink
-// transfers on the copy engines, a local add + LayerNorm kernel between them) runs on that half-batch's own
-// high-priority stream as soon as its partial sums are complete, i.e. beside the OTHER half-batch's next phase, and
-// the phase that consumes its LayerNorm output waits for it through an event.  Each half-batch has its own flag set,
-// epoch counter and receive buffer.
+// Row-parallel GEMM of the peer-memory path: output row m of the `rows` rows of this reduction goes to the rank that
+// owns it, into slot `my rank` of that rank's receive region (tp_fused.h: TpPeerView::recv).
+void tp_route_rows(OasrEngine* e, GemmArgs& a, long long recv_off, long long rows) {
+  const int W = e->tp_world;
+  const TpShare mine = tp_share(rows, e->tp_first, W);
+  a.out = nullptr;
+  a.route_n = W;
+  a.route_per = (int)mine.per;
+  for (int q = 0; q < W; ++q)
+    a.route_base[q] = e->tp_view.recv[q] + recv_off + (long long)e->tp_first * mine.slot_rows * e->cfg.d_model;
+}
+
+// Tensor-parallel encoder layers, peer-memory path, B >= 2: the batch is cut into two half-batches of windows
+// (attention never crosses a window).  All compute kernels stay on the caller's stream, in the order
+// P1(h0) P1(h1) P2(h0) P2(h1) per layer (P1 = QKV, attention, out-proj; P2 = FFN1, FFN2).  The row-parallel GEMMs
+// (out-proj, FFN2) PUSH their partial sums into the owners' receive regions from their epilogues (route_rows); the
+// tail of a half-batch's reduction (tp_push_reduce_layernorm: flag hand-shake, add + LayerNorm + LN rows pushed to
+// every rank, flag hand-shake) runs on that half-batch's own high-priority stream as soon as its GEMM has finished,
+// i.e. beside the OTHER half-batch's next phase, and the phase that consumes its LayerNorm output waits for it through
+// an event.  Each half-batch has its own flag set, epoch counter and receive region.
 int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int stop_stage, cudaStream_t st) {
   const OasrConfig& c = e->cfg;
   const int d = c.d_model, F = c.d_ffn, H = c.n_heads, hd = d / H;
@@ -410,39 +420,17 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
   const long long r0[2] = {0, (long long)Bh[0] * T};
   const long long Mh[2] = {(long long)Bh[0] * T, (long long)Bh[1] * T};
   const long long M = Mh[0] + Mh[1];
-  {
-    const long long share = Mh[0] - (Mh[0] / W) * (W - 1);
-    const size_t need = (size_t)(W - 1) * (size_t)share * d * 2;
-    if (need > e->tp_recv_bytes) {   // one buffer per half-batch: their reductions may be in flight together
-      if (e->tp_recv) cudaFree(e->tp_recv);
-      e->tp_recv = nullptr;
-      e->tp_recv_bytes = 0;
-      void* ptr = nullptr;
-      OASR_TRY(dev_alloc(&ptr, 2 * need, false));
-      e->tp_recv = reinterpret_cast<__nv_bfloat16*>(ptr);
-      e->tp_recv2 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ptr) + need);
-      e->tp_recv_bytes = need;
-    }
-  }
-  static const bool timing = std::getenv("OASR_TP_TIMING") != nullptr;
-  static int timing_calls = 0;
-  static cudaEvent_t timing_ev[7] = {};
+  // receive regions of the two half-batches inside every rank's receive buffer: [source][slot_rows][d] each
+  const long long recv_off[2] = {0, (long long)W * tp_share(Mh[0], 0, W).slot_rows * d};
+  auto route = [&](GemmArgs& a, int h) { tp_route_rows(e, a, recv_off[h], Mh[h]); };
   auto reduce_ln = [&](int h, const float* g, const float* bta, bool bcast_x) -> int {
-    // copy-engine mode: each half-batch has its own stream, flag set and receive buffer, so that the transfers of one
-    // reduction run beside the local kernel of the other
+    // each half-batch has its own stream, flag set and receive region: the tail of one reduction runs beside the
+    // compute of the other half-batch
     cudaStream_t cs = h == 1 ? e->tp_comm_stream2 : e->tp_comm_stream;
     OASR_CUDA_CHECK(cudaEventRecord(e->tp_ev_compute[h], st));
     OASR_CUDA_CHECK(cudaStreamWaitEvent(cs, e->tp_ev_compute[h], 0));
-    {
-      cudaEvent_t* tr = nullptr;
-      if (timing && ++timing_calls == 9) {   // one call in the steady state of the first forward
-        for (auto& ev : timing_ev) OASR_CUDA_CHECK(cudaEventCreate(&ev));
-        tr = timing_ev;
-        OASR_CUDA_CHECK(cudaEventRecord(timing_ev[6], st));   // the compute stream at the moment the call is issued
-      }
-      if (h == 0) OASR_TRY(tp_dma_reduce_layernorm(e->tp_view, r0[h], Mh[h], d, g, bta, ++e->tp_epoch, bcast_x, e->tp_recv, cs, tr));
-      else OASR_TRY(tp_dma_reduce_layernorm(e->tp_view2, r0[h], Mh[h], d, g, bta, ++e->tp_epoch2, bcast_x, e->tp_recv2, cs, tr));
-    }
+    if (h == 0) OASR_TRY(tp_push_reduce_layernorm(e->tp_view, recv_off[0], r0[0], Mh[0], d, g, bta, ++e->tp_epoch, bcast_x, cs));
+    else OASR_TRY(tp_push_reduce_layernorm(e->tp_view2, recv_off[1], r0[1], Mh[1], d, g, bta, ++e->tp_epoch2, bcast_x, cs));
     OASR_CUDA_CHECK(cudaEventRecord(e->tp_ev_reduce[h], cs));
     return OASR_OK;
   };
@@ -476,14 +464,14 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       {
         GemmArgs a = GemmArgs::plain(e->att + r0[h] * d_loc, (int)Mh[h], d_loc, d_loc, w.s_wo[0], d);
         a.bias = add_bias ? w.bo : nullptr;
-        a.out = e->part_bf16 + r0[h] * d;   // this rank's partial sum, rounded to bf16: what crosses NVLink
         a.ldo = d;
-        a.epilogue = EPI_BF16;
+        a.epilogue = EPI_BF16;   // this rank's partial sums, rounded to bf16, pushed to the ranks that own the rows
+        route(a, h);
         OASR_TRY(gemm_bf16_tcgen05(a, st));
       }
       OASR_TRY(reduce_ln(h, w.ffn_ln_g, w.ffn_ln_b, false));
       pending[h] = true;
-      e->launches += 6;   // 3 compute kernels + ready signal/wait, local add + LayerNorm, done signal/wait
+      e->launches += 6;   // 3 compute kernels + ready signal/wait, add + LayerNorm + push, done signal/wait
     }
     const bool last = l + 1 == c.n_layers;
     const float* g = last ? e->final_ln_g : e->layers[l + 1].attn_ln_g;
@@ -504,9 +492,9 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
       {
         GemmArgs a = GemmArgs::plain(e->ffn + r0[h] * F_loc, (int)Mh[h], F_loc, F_loc, w.s_w2[0], d);
         a.bias = add_bias ? w.b2 : nullptr;
-        a.out = e->part_bf16 + r0[h] * d;
         a.ldo = d;
         a.epilogue = EPI_BF16;
+        route(a, h);
         OASR_TRY(gemm_bf16_tcgen05(a, st));
       }
       OASR_TRY(reduce_ln(h, g, bta, want_hidden));
@@ -521,17 +509,6 @@ int tp_layers_overlapped(OasrEngine* e, int B, int T, float* hidden_out, int sto
   }
   OASR_TRY(wait_reduce(0));
   OASR_TRY(wait_reduce(1));
-  if (timing && timing_calls >= 9 && timing_ev[0] != nullptr) {
-    OASR_CUDA_CHECK(cudaStreamSynchronize(st));
-    OASR_CUDA_CHECK(cudaStreamSynchronize(e->tp_comm_stream));
-    OASR_CUDA_CHECK(cudaStreamSynchronize(e->tp_comm_stream2));
-    float ms[6] = {};
-    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], timing_ev[i], timing_ev[i + 1]);
-    cudaEventElapsedTime(&ms[5], timing_ev[6], timing_ev[0]);
-    fprintf(stderr, "oasr tp timing (rank %d): issue->start %.3f | ready wait %.3f | dma in %.3f | local %.3f | dma out %.3f | "
-            "done wait %.3f ms\n", e->tp_first, ms[5], ms[0], ms[1], ms[2], ms[3], ms[4]);
-    for (auto& ev : timing_ev) { cudaEventDestroy(ev); ev = nullptr; }
-  }
   if (hidden_out != nullptr) {
     prof_mark(e, OASR_PROF_LAYERNORM, st);
     OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, e->final_ln_g, e->final_ln_b, e->lnbuf, hidden_out, st));
@@ -662,14 +639,12 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
 
   // a14
   const float scale = 1.0f / sqrtf((float)hd);
-  // OASR_TP_OVERLAP = dma (default): the reductions' transfers run on the copy engines beside the other half-batch's
-  // GEMMs | off: one fused peer-memory kernel per reduction, nothing beside it (also what a single window takes)
-  static const int tp_overlap = [] {
+  // OASR_TP_OVERLAP=off: no half-batch pipeline - every reduction's tail runs on the compute stream with nothing
+  // beside it (what a single window takes anyway; scripts/tp_check.py covers both through the batch size)
+  static const bool overlap = [] {
     const char* v = std::getenv("OASR_TP_OVERLAP");
-    if (v == nullptr) return -1;
-    return std::strcmp(v, "dma") == 0 ? 1 : 0;
+    return v == nullptr || std::strcmp(v, "off") != 0;
   }();
-  const bool overlap = tp_overlap < 0 ? true : tp_overlap == 1;
   if (e->tp_world > 1 && e->tp_fused && e->tp_local == 1 && B >= 2 && c.n_layers > 0 && overlap) {
     OASR_TRY(tp_layers_overlapped(e, B, T, hidden_out, stop_stage, st));
     if (stop_stage >= 4 && stop_stage < 4 + c.n_layers) {
@@ -719,7 +694,10 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
           GemmArgs a = GemmArgs::plain(e->att, (int)M, d_loc, d_loc, w.s_wo[s], d);
           a.bias = add_bias ? w.bo : nullptr;
           a.ldo = d;
-          if (bf16_part) {   // every shard's partial sum on its own, rounded to bf16 (what crosses NVLink in a real run)
+          if (e->tp_fused) {          // pushed to the owners' receive regions from the epilogue
+            a.epilogue = EPI_BF16;
+            tp_route_rows(e, a, 0, M);
+          } else if (bf16_part) {     // every shard's partial sum on its own, rounded to bf16 as in a real run
             a.out = e->part_bf16 + s * e->part_shard_stride;
             a.epilogue = EPI_BF16;
           } else {
@@ -731,9 +709,9 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
         }
         e->launches += 3;
       }
-      if (e->tp_fused) {   // all-reduce + residual + LayerNorm + redistribution in one kernel over peer memory
+      if (e->tp_fused) {   // the partial sums are in the owners' receive regions: add + LayerNorm + LN rows to every rank
         prof_mark(e, OASR_PROF_ALLREDUCE, st);
-        OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, w.ffn_ln_g, w.ffn_ln_b, ++e->tp_epoch, false, st));
+        OASR_TRY(tp_push_reduce_layernorm(e->tp_view, 0, 0, M, d, w.ffn_ln_g, w.ffn_ln_b, ++e->tp_epoch, false, st));
       } else if (e->tp_emulated) {
         prof_mark(e, OASR_PROF_ALLREDUCE, st);
         OASR_TRY(emulated_reduce(w.ffn_ln_g, w.ffn_ln_b));
@@ -759,7 +737,10 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
           GemmArgs a = GemmArgs::plain(e->ffn, (int)M, F_loc, F_loc, w.s_w2[s], d);
           a.bias = add_bias ? w.b2 : nullptr;
           a.ldo = d;
-          if (bf16_part) {
+          if (e->tp_fused) {
+            a.epilogue = EPI_BF16;
+            tp_route_rows(e, a, 0, M);
+          } else if (bf16_part) {
             a.out = e->part_bf16 + s * e->part_shard_stride;
             a.epilogue = EPI_BF16;
           } else {
@@ -778,7 +759,7 @@ int forward_eager(OasrEngine* e, const float* wave_in, int64_t wave_stride, cons
       if (e->tp_fused) {
         prof_mark(e, OASR_PROF_ALLREDUCE, st);
         const bool want_hidden = last && hidden_out != nullptr;   // parity runs: the fp32 LayerNorm output of all rows
-        OASR_TRY(tp_fused_reduce_layernorm(e->tp_view, M, d, g, bta, ++e->tp_epoch, want_hidden, st));
+        OASR_TRY(tp_push_reduce_layernorm(e->tp_view, 0, 0, M, d, g, bta, ++e->tp_epoch, want_hidden, st));
         if (want_hidden) {
           prof_mark(e, OASR_PROF_LAYERNORM, st);
           OASR_TRY(layernorm_rows(e->x, 0, 0, 1, (int)M, d, g, bta, e->lnbuf, hidden_out, st));
@@ -954,7 +935,6 @@ void oasr_destroy(OasrHandle h) {
   if (h->graph_join) cudaEventDestroy(h->graph_join);
   if (h->tp_comm_stream) cudaStreamDestroy(h->tp_comm_stream);
   if (h->tp_comm_stream2) cudaStreamDestroy(h->tp_comm_stream2);
-  if (h->tp_recv) cudaFree(h->tp_recv);
   for (int i = 0; i < 2; ++i) {
     if (h->tp_ev_compute[i]) cudaEventDestroy(h->tp_ev_compute[i]);
     if (h->tp_ev_reduce[i]) cudaEventDestroy(h->tp_ev_reduce[i]);
@@ -1094,7 +1074,9 @@ int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out) {
   h->tp_x_bytes = M * d * 4;
   h->tp_off_ln = up(h->tp_x_bytes);
   h->tp_off_part = h->tp_off_ln + up(M * std::max<size_t>(512, d) * 2);
-  h->tp_off_flags = h->tp_off_part + up(M * d * 2);   // partial sums travel in bf16
+  // receive region: [source][slot rows][d] bf16 per half-batch; the slots of a half-batch cover its rows plus at most
+  // `world` rows of rounding each
+  h->tp_off_flags = h->tp_off_part + up((M + 4 * TP_MAX_WORLD * TP_MAX_WORLD) * d * 2);
   const size_t total = h->tp_off_flags + 1024;   // two flag sets, 512 B apart (one per half-batch in overlap mode)
   OASR_TRY(dev_alloc(&h->tp_arena, total, true));
   OASR_CUDA_CHECK(cudaDeviceSynchronize());
@@ -1127,11 +1109,10 @@ int oasr_tp_ipc_import(OasrHandle h, const void* handles) {
     uint8_t* base = reinterpret_cast<uint8_t*>(h->tp_peer_base[q]);
     v.x[q] = reinterpret_cast<float*>(base);
     v.ln[q] = reinterpret_cast<__nv_bfloat16*>(base + h->tp_off_ln);
-    v.part[q] = reinterpret_cast<const __nv_bfloat16*>(base + h->tp_off_part);
+    v.recv[q] = reinterpret_cast<__nv_bfloat16*>(base + h->tp_off_part);
     v.ready[q] = reinterpret_cast<unsigned long long*>(base + h->tp_off_flags);
     v.done[q] = v.ready[q] + TP_MAX_WORLD;
   }
-  v.cta_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(h->tp_arena) + h->tp_off_flags + 2 * TP_MAX_WORLD * 8);
   if (h->tp_err_host == nullptr) {
     OASR_CUDA_CHECK(cudaHostAlloc((void**)&h->tp_err_host, 64, cudaHostAllocMapped));
     *h->tp_err_host = 0;
@@ -1144,7 +1125,6 @@ int oasr_tp_ipc_import(OasrHandle h, const void* handles) {
     h->tp_view2.ready[q] = v.ready[q] + 64;
     h->tp_view2.done[q] = v.done[q] + 64;
   }
-  h->tp_view2.cta_counter = v.cta_counter + 128;
   h->tp_fused = true;
   return OASR_OK;
 }

@@ -51,6 +51,13 @@ struct GemmArgs {
   const int* n_valid = nullptr;   // EPI_F32: rows with (row % frames_per_seq) >= n_valid[row / frames_per_seq] -> 0
   int frames_per_seq = 0;
   int epilogue = EPI_BF16;
+  // EPI_BF16 on a plain GEMM only - ROUTED rows (tensor parallelism, tp_fused.cu): output row m does not go to `out`
+  // but to its owner o = min(m / route_per, route_n - 1), at route_base[o] + (m - o * route_per) * ldo.  The bases are
+  // peer-mapped (CUDA IPC) receive buffers: a rank's partial sums leave the epilogue straight for the ranks that reduce
+  // them, as posted NVLink stores spread over the GEMM's duration - no separate transfer, nothing to pull.
+  int route_n = 0;
+  int route_per = 0;
+  void* route_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // plain row-major GEMM: A [M, K] with leading dimension lda
   static GemmArgs plain(const void* A, int M, int K, long long lda, const void* W, int N) {

@@ -44,6 +44,8 @@ struct GemmKernelParams {
   unsigned long long* argmax;
   const int* n_valid;
   int frames_per_seq;
+  int route_n, route_per;            // EPI_BF16: rows routed to their owners' (peer) buffers, see GemmArgs
+  __nv_bfloat16* route_base[8];
 };
 
 // CG = CTAs cooperating on one tile (tcgen05 cta_group): 1, or 2 = a CTA pair computing a 256 x BN tile with each
@@ -400,12 +402,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int j = 0; j < 4; ++j) srow[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
         __syncwarp();
         const int n = col0 + t_piece * 8;
-        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row0 * p.ldo + gcol + n;
+        if (p.route_n > 0) {   // warp-uniform: every row goes to the rank that owns it (peer memory)
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + t_r8;
-          const uint4 val = *reinterpret_cast<const uint4*>(stage + row * STAGE_LD + t_piece * 4);
-          if (row < rows_valid && n < p.N) *reinterpret_cast<uint4*>(obase + (long long)row * p.ldo) = val;
+          for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + t_r8;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + row * STAGE_LD + t_piece * 4);
+            if (row < rows_valid && n < p.N) {
+              const int m = (int)out_row0 + row;
+              const int o = min(m / p.route_per, p.route_n - 1);
+              *reinterpret_cast<uint4*>(p.route_base[o] + (long long)(m - o * p.route_per) * p.ldo + gcol + n) = val;
+            }
+          }
+        } else {
+          __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row0 * p.ldo + gcol + n;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int row = it * 8 + t_r8;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage + row * STAGE_LD + t_piece * 4);
+            if (row < rows_valid && n < p.N) *reinterpret_cast<uint4*>(obase + (long long)row * p.ldo) = val;
+          }
         }
         __syncwarp();
       };
@@ -677,6 +692,9 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.argmax = a.argmax;
   p.n_valid = a.n_valid;
   p.frames_per_seq = a.frames_per_seq;
+  p.route_n = a.route_n;
+  p.route_per = a.route_per;
+  for (int i = 0; i < 8; ++i) p.route_base[i] = reinterpret_cast<__nv_bfloat16*>(a.route_base[i]);
   if (p.total_tiles == 0) return OASR_OK;
 
   // A: {a_inner, P, U, batches, groups}; a unit-extent dimension still needs a legal (16-byte multiple) stride
@@ -785,8 +803,16 @@ int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
                "gemm: operands must be 16-byte aligned");
   OASR_REQUIRE(a.N % 8 == 0 || (a.epilogue == EPI_ARGMAX && a.N % 4 == 0), "gemm: N must be a multiple of 8 (4 for arg-max)");
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(a.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+  if (a.route_n > 0) {
+    OASR_REQUIRE(a.epilogue == EPI_BF16 && a.batches == 1 && a.groups == 1 && a.taps == 1 && a.route_n <= 8 &&
+                     a.route_per > 0 && a.out_batch_rows == 0,
+                 "gemm: routed rows need a plain bf16 GEMM, at most 8 owners and a positive share");
+    for (int i = 0; i < a.route_n; ++i)
+      OASR_REQUIRE(a.route_base[i] != nullptr && (reinterpret_cast<uintptr_t>(a.route_base[i]) & 15) == 0,
+                   "gemm: routed destinations must be 16-byte aligned");
+  }
   if (a.epilogue != EPI_ARGMAX) {
-    OASR_REQUIRE(a.out != nullptr && a.ldo >= a.N * a.groups, "gemm: output missing");
+    OASR_REQUIRE((a.out != nullptr || a.route_n > 0) && a.ldo >= a.N * a.groups, "gemm: output missing");
     OASR_REQUIRE(a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0,
                  "gemm: output rows must be 16-byte aligned");
   }
