@@ -31,6 +31,9 @@ struct GemmKernelParams {
   int rows_per_batch, batches, groups, N;
   int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
   int kb_per_tap, P;       // k-block -> (tap, column block); tap -> (parity, position offset)
+  int k16_last;            // K = 16 steps that hold data in the LAST k-block of a tap (1 .. 4): the columns beyond
+                           // a_inner are zero padding (pos-conv at 80 channels per group: 64 + 16 of 128), and
+                           // multiplying zeros cost 3 of every 8 MMAs there
   int umma_n;              // N of one tcgen05.mma (<= 256, multiple of 16)
   int b_box_rows;          // rows of W fetched per TMA box
   uint32_t stage_tx_bytes; // bytes landing on a full barrier per stage
@@ -220,17 +223,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
+        int kt = 0;   // k-block within the tap
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_lo = smem_lo + s * (C::STAGE_BYTES >> 4);
           const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
+          const int k16 = kt + 1 == p.kb_per_tap ? p.k16_last : BK / UMMA_K;   // warp-uniform
+          if (++kt == p.kb_per_tap) kt = 0;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + k * (UMMA_K * 2 >> 4));
             const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + k * (UMMA_K * 2 >> 4));
             const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-            if (issuer) {
+            if (issuer && k < k16) {
               if constexpr (CG == 2) umma_ss_cg2(d_tmem, adesc, bdesc, idesc, acc);
               else umma_ss(d_tmem, adesc, bdesc, idesc, acc);
             }
@@ -677,6 +683,11 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.total_tiles = p.m_tiles_per_batch * a.batches * a.groups * p.n_tiles;
   p.kb_per_tap = k_pad / BK;
   p.k_blocks = p.kb_per_tap * a.taps;
+  {
+    const int tail = a.a_inner - (p.kb_per_tap - 1) * BK;   // valid columns of a tap's last k-block (<= BK)
+    p.k16_last = tail >= BK ? BK / UMMA_K : (tail + UMMA_K - 1) / UMMA_K;
+    if (p.k16_last < 1) p.k16_last = 1;
+  }
   p.P = a.P;
   const int n_cap = a.N < BN ? ((a.N + 15) / 16) * 16 : BN;   // columns one tile really computes
   p.umma_n = n_cap;
