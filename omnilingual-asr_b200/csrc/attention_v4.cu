@@ -45,7 +45,7 @@ struct Attn4Params {
   const int* n_frames;
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
-  int start_offset;   // tile B issues its first S this many cycles after tile A (OASR_ATT4_OFFSET overrides)
+  int start_offset;   // tile B issues its first S this many cycles after tile A
 };
 constexpr int TRACE_EVENTS = 128;   // per role: 0 MMA warp, 1 softmax warp 0 (tile A), 2 softmax warp 4 (tile B)
 // Tracing is a compile-time option (-DOASR_ATT_TRACING): even a never-taken stamp costs the softmax warps issue
@@ -471,11 +471,7 @@ int attention_bf16_v4(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.trace = nullptr;
-  static const int start_offset = [] {
-    const char* e = std::getenv("OASR_ATT4_OFFSET");
-    return e != nullptr ? std::atoi(e) : 1200;   // half a block period (measured best of 0 / 400 / 800 / 1200)
-  }();
-  p.start_offset = start_offset;
+  p.start_offset = 1200;   // half a block period (measured best of 0 / 400 / 800 / 1200)
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
   if (trace_path != nullptr) {
     OASR_CUDA_CHECK(cudaMalloc(&p.trace, 3 * TRACE_EVENTS * sizeof(long long)));

@@ -43,7 +43,7 @@ struct Attn7Params {
   const int* n_frames;
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
-  int start_offset;   // tile X issues its first S this many cycles after tile X-1 (OASR_ATT6_OFFSET overrides)
+  int start_offset;   // tile X issues its first S this many cycles after tile X-1
   int relay;          // exponential phases in relay (see the softmax warps): 0 off, n: hand on after n 16-column pieces
 };
 constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
@@ -589,11 +589,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_frames = n_frames;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.trace = nullptr;
-  static const int start_offset = [] {
-    const char* e = std::getenv("OASR_ATT6_OFFSET");
-    return e != nullptr ? std::atoi(e) : START_OFFSET_CYCLES;
-  }();
-  p.start_offset = start_offset;
+  p.start_offset = START_OFFSET_CYCLES;
   static const int relay = [] {
     const char* e = std::getenv("OASR_ATT_RELAY");   // 0: free-running tiles; 1 / 2: hand on after 16 / 32 columns
     return e != nullptr ? std::atoi(e) : 1;
@@ -608,12 +604,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   OASR_REQUIRE((long long)p.n_qt * H * B < (1ll << 31), "attention: too many work items");
   p.n_items = p.n_qt * H * B;
   const int num_sms = device_sm_count();
-  static const int grid_override = [] {
-    const char* e = std::getenv("OASR_ATT7_GRID");   // experiments: CTAs to launch (default: one per SM)
-    return e != nullptr ? std::atoi(e) : 0;
-  }();
-  const int want = grid_override > 0 ? grid_override : num_sms;
-  dim3 grid(p.n_items < want ? p.n_items : want);
+  dim3 grid(p.n_items < num_sms ? p.n_items : num_sms);   // persistent: one CTA per SM
   cudaError_t attr_err = cudaSuccess;
   // OASR_ATT_POLY = 3: every third pair of exponentials on the FMA pipe (default 0: all on MUFU.EX2; measured slower
   // in every shape so far, profiles/r2_notes.md; tests/test_gpu_kernels.py::test_attention_poly_settings_agree)

@@ -783,19 +783,11 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   return OASR_OK;
 }
 
-// CTA pairs whenever a tile spans full 256-column MMAs (every encoder / FE / CTC GEMM); OASR_GEMM_CG=1 forces
-// the single-CTA kernel (debugging aid).
-bool use_pairs() {
-  static const bool v = [] {
-    const char* e = std::getenv("OASR_GEMM_CG");
-    return !(e != nullptr && e[0] == '1');
-  }();
-  return v;
-}
-
+// CTA pairs whenever a tile spans full 256-column MMAs (every encoder / FE / CTC GEMM), single CTAs for narrower outputs
+// (pos-conv groups, the small test shapes)
 template <int BN, int EPI>
 int launch(const GemmArgs& a, cudaStream_t stream) {
-  if (BN >= 256 && a.N >= BN && use_pairs()) return launch_cg<BN, EPI, 2>(a, stream);
+  if (BN >= 256 && a.N >= BN) return launch_cg<BN, EPI, 2>(a, stream);
   return launch_cg<BN, EPI, 1>(a, stream);
 }
 

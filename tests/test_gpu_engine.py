@@ -568,3 +568,19 @@ def test_small_batch_graph_replay_equals_eager_launches(device):
             assert (g.frame_ids[b, :nf] == ref.frame_ids[b, :nf]).all()
             assert (np.asarray(g.token_ids[b]) == np.asarray(ref.token_ids[b])).all()
             assert (np.asarray(g.token_frames[b]) == np.asarray(ref.token_frames[b])).all()
+
+
+def test_graph_switch_off_gives_the_same_ids(device, tmp_path):
+    """OASR_GRAPH_MAX_B=0 disables the CUDA-graph replay of small batches: same frame ids, same launch accounting."""
+    import os
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    outs = []
+    for v in ("8", "0"):
+        out = tmp_path / f"graph_{v}.npy"
+        r = subprocess.run([sys.executable, str(root / "scripts" / "engine_variant.py"), str(out)],
+                           env=dict(os.environ, OASR_GRAPH_MAX_B=v), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out))
+    assert (outs[0] == outs[1]).all()

@@ -354,6 +354,14 @@ def test_attention_shapes_agree(device, tmp_path, hd):
         assert same > 0.99 and worst < 1e-2
 
 
+def test_attention_relay_switch(device, tmp_path):
+    """OASR_ATT_RELAY (exponential phases of the tiles kept apart by named barriers: 0 free-running, 1 default, 2):
+    scheduling only - the outputs are bit-identical."""
+    ref = _attention_variant(tmp_path, {"OASR_ATT_RELAY": "0"}, 3, 700, 4, 80)
+    for r in ("1", "2"):
+        assert (_attention_variant(tmp_path, {"OASR_ATT_RELAY": r}, 3, 700, 4, 80) == ref).all()
+
+
 def test_attention_env_switch_v4(device, tmp_path):
     """OASR_ATTN=4 forces the two-tile kernel (the default above head_dim 80) at head_dim 80: same result as v7."""
     a = _attention_variant(tmp_path, {"OASR_ATTN": "7"}, 2, 500, 4, 80)
