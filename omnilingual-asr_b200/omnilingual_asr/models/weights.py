@@ -44,6 +44,41 @@ def random_weights(cfg: CtcModelConfig, seed: int = 0, device: Any = "cpu") -> D
     return out
 
 
+_HEAD_KEYS = ("num_attention_heads", "num_encoder_attn_heads", "encoder_attention_heads", "n_heads", "num_heads")
+
+
+def check_head_count(cfg: CtcModelConfig, meta: Any) -> None:
+    """The head count changes no tensor shape, so a checkpoint loads cleanly under a wrong one and then transcribes
+    wrongly.  The 16 heads of the 2048-wide cards (3B, 7B) come from SURVEY.md's recollection of upstream's arch
+    registry, not from a file available here: when a checkpoint carries its own head count (a config / metadata
+    mapping with one of the usual keys, nested or not) it must agree with `cfg`; when a REAL checkpoint of a 2048-wide
+    model carries none, the caller is told what is being assumed."""
+    found = None
+
+    def walk(m: Any, depth: int) -> None:
+        nonlocal found
+        if found is not None or depth > 3 or not isinstance(m, Mapping):
+            return
+        for k in _HEAD_KEYS:
+            if k in m and isinstance(m[k], (int, np.integer)):
+                found = int(m[k])
+                return
+        for k, v in m.items():
+            if isinstance(v, Mapping) and not (isinstance(k, str) and k in ("model", "state_dict")):
+                walk(v, depth + 1)
+
+    walk(meta, 0)
+    if found is not None:
+        if found != cfg.n_heads:
+            raise ValueError(f"checkpoint says {found} attention heads, model card {cfg.name} is configured with "
+                             f"{cfg.n_heads}: pass a CtcModelConfig with n_heads={found}")
+    elif cfg.d_model >= 2048:
+        import warnings
+        warnings.warn(f"{cfg.name}: the checkpoint carries no head count; assuming {cfg.n_heads} heads "
+                      f"(head_dim {cfg.d_model // cfg.n_heads}), which is upstream's value as recalled in SURVEY.md, not "
+                      "verified offline - pass a CtcModelConfig with the right n_heads if it differs", stacklevel=3)
+
+
 def resolve_weights(cfg: CtcModelConfig, weights: Any, seed: int, device: Any) -> Mapping[str, torch.Tensor]:
     if isinstance(weights, str) and weights == "random":
         return random_weights(cfg, seed, device)
@@ -52,6 +87,7 @@ def resolve_weights(cfg: CtcModelConfig, weights: Any, seed: int, device: Any) -
         if not p.exists():
             raise ValueError(f"checkpoint not found: {p}")
         sd = torch.load(str(p), map_location="cpu", weights_only=True)
+        check_head_count(cfg, sd)
         if isinstance(sd, Mapping) and "model" in sd and isinstance(sd["model"], Mapping):
             sd = sd["model"]
         return convert_state_dict(sd, cfg)

@@ -95,3 +95,20 @@ def test_checkpoint_file_in_hf_layout_resolves(tmp_path):
     w = W.resolve_weights(cfg, str(path), seed=0, device="cpu")
     for n in native:
         assert torch.equal(w[n], native[n])
+
+
+def test_checkpoint_head_count_is_checked_when_present():
+    """the head count changes no tensor shape; a checkpoint that states its own must agree with the card,
+    and a 2048-wide checkpoint without one triggers a warning naming the assumption."""
+    import warnings
+    from omnilingual_asr.models.config import get_model_config
+    from omnilingual_asr.models.weights import check_head_count
+    c3 = get_model_config("omniASR_CTC_3B")
+    check_head_count(c3, {"config": {"num_attention_heads": 16}, "model": {}})
+    with pytest.raises(ValueError, match="32 attention heads"):
+        check_head_count(c3, {"model_config": {"encoder": {"num_encoder_attn_heads": 32}}})
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        check_head_count(c3, {"model": {}})
+        check_head_count(get_model_config("omniASR_CTC_1B"), {"model": {}})     # 1280-wide: nothing to warn about
+    assert len(w) == 1 and "assuming 16 heads" in str(w[0].message)
