@@ -1,11 +1,9 @@
 // Pieces shared by the attention kernels (attention_v4.cu: two query tiles per CTA; attention_v6.cu: three): operand
 // chunking for any head_dim % 16 == 0, UMMA descriptor halves, and the per-row softmax with an integer log2-domain
 // reference (a reference move rescales P, the row sum and O by an exact power of two).
-// Every POLY_EVERY-th pair of exponentials of a row is evaluated on the FMA pipe (ex2_poly2: Cody-Waite range reduction
-// folded into the score FMA + a degree-4 polynomial) instead of MUFU.EX2.  Round 1 tried this with two softmax warps per
-// scheduler, found the kernel bound by issue latency (MUFU at 48 %) and dropped it; with three warps per scheduler the
-// MUFU pipe is the binding one (ncu: XU 66 %, the warps' exponential phases collide), so a third of the exponentials
-// now leaves it (profiles/r2_notes.md).
+// Moving a share of the exponentials to the FMA pipe (Cody-Waite range reduction folded into the score FMA + a degree-4
+// polynomial, 2.6e-6 relative) was measured in both rounds - round 2 in four kernel shapes - and made the kernel slower
+// in proportion to the instructions it added (profiles/r2_notes.md); it is not in the tree.
 #pragma once
 #include "ptx.cuh"
 
@@ -53,40 +51,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float2 fsub2(float2 a, float2 b) {
-  uint64_t ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-
-// 2^(s c - m) for two scores without the MUFU pipe.  m is integer-valued (the row's log2 reference), so
-//   t  = fma(s, c, MAGIC - m)      MAGIC = 1.5 * 2^23: t = MAGIC + n with n = round(s c - m), in ONE rounding
-//   r  = fma(s, c, -(m + n))       the reduced argument in [-1/2, 1/2], again one rounding ((m + n) = t - (MAGIC - m) is exact)
-//   2^r = degree-4 minimax polynomial (relative error 2.6e-6: 1/750 of a bf16 half-ulp, 0.03 % of the rounded P differ)
-//   2^n = added into the exponent field: bits(p) + (bits(t) << 23) - MAGIC's own bits fall off the top of the word.
-// n is clamped at -120 (the result is then < 2^-117, nothing next to a row whose largest P is >= 1/2; the clamp also
-// keeps the exponent field from borrowing when the polynomial is evaluated outside its interval); the caller guarantees
-// s c - m <= REF_MARGIN + 1, so there is no upper clamp.
-constexpr float EX2_MAGIC = 12582912.f;
-__device__ __forceinline__ float2 ex2_poly2(float2 s, float2 c2, float m_ref) {
-  const float km = EX2_MAGIC - m_ref;
-  float2 t = ffma2(s, c2, make_float2(km, km));
-  t.x = fmaxf(t.x, EX2_MAGIC - 120.f);
-  t.y = fmaxf(t.y, EX2_MAGIC - 120.f);
-  const float2 r = ffma2(s, c2, fsub2(make_float2(km, km), t));   // km - t = -(m + n)
-  float2 p = ffma2(make_float2(0.009570094756782055f, 0.009570094756782055f), r,
-                   make_float2(0.05591785907745361f, 0.05591785907745361f));
-  p = ffma2(p, r, make_float2(0.240247443318367f, 0.240247443318367f));
-  p = ffma2(p, r, make_float2(0.6931217908859253f, 0.6931217908859253f));
-  p = ffma2(p, r, make_float2(0.9999992847442627f, 0.9999992847442627f));
-  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(t.x) << 23)),
-                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(t.y) << 23)));
-}
-
 __device__ __forceinline__ uint32_t bf16x2_scale(uint32_t v, uint32_t f2) {
   uint32_t r;
   asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(f2));
@@ -134,8 +98,7 @@ __device__ __forceinline__ void move_reference(float need, RowState<HD>& rs, uin
 }
 
 // W scores of a row (columns [BASE, BASE+W) of the block): reference check, P = 2^(s c - m_ref) -> pk, sums.
-// POLY_EVERY > 0: pair number k of the block (columns 2k, 2k + 1) goes to the FMA pipe when k % POLY_EVERY == POLY_EVERY - 1.
-template <int HD, int BASE, int W, bool MASKED, int PKN, int POLY_EVERY = 0>
+template <int HD, int BASE, int W, bool MASKED, int PKN>
 __device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, float c, RowState<HD>& rs,
                                               uint32_t (&pk)[PKN]) {
   float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
@@ -152,16 +115,8 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, floa
   const float2 c2 = make_float2(c, c), nm2 = make_float2(-rs.m_ref, -rs.m_ref);
 #pragma unroll
   for (int i = 0; i < W; i += 2) {
-    float p0, p1;
-    if (POLY_EVERY > 0 && ((BASE + i) >> 1) % (POLY_EVERY > 0 ? POLY_EVERY : 1) == POLY_EVERY - 1) {
-      const float2 e = ex2_poly2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, rs.m_ref);
-      p0 = e.x;
-      p1 = e.y;
-    } else {
-      const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
-      p0 = ex2(x.x);
-      p1 = ex2(x.y);
-    }
+    const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
+    float p0 = ex2(x.x), p1 = ex2(x.y);
     if (MASKED) {
       if (BASE + i >= ncols) p0 = 0.f;
       if (BASE + i + 1 >= ncols) p1 = 0.f;

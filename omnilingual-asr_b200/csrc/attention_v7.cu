@@ -2,16 +2,10 @@
 // CTA per SM walking a static list of (query group, head, window) work items; NT query tiles of 128 rows per CTA, one
 // MMA-issuing warp per tile, the K/V ring, the barrier phases and the tile stagger running on across items.
 //
-// Three shapes are instantiated <NT query tiles, BKV keys per block, SST S buffers per tile> (OASR_ATT_CFG):
-//   3,48,1  round 1's shape: S single-buffered, so S(j+1) can only be issued when the softmax warps have read S(j), and
-//           the P buffer is known to be free through s_full(j+1).  The softmax warps' loop therefore carries the
-//           issuer's round trip (s_free -> wake -> 5 MMAs -> tensor pipe -> s_full, ~700 cycles) beside their
-//           exponentials: measured period ~1650 cycles per 48-key block against a MUFU floor of 1152.
-//   2,64,2  S DOUBLE-buffered (TMEM: 2 x 2 x 64 S + 2 x 32 P + 2 x 80 O = 480 columns): S(j+2) is issued right after
-//           P.V(j), a whole block ahead of its use, so the softmax loop only ever waits for barriers that completed long
-//           ago; 64-key blocks halve the per-key share of the fixed hand-off cost; 352 threads leave 168 registers each.
-//   3,32,2  the same with three tiles and 32-key blocks (480 columns as well).
-// TMEM columns: S[tile][stage] (BKV each) | P[tile] (BKV/2 used, rounded to 16) | O[tile] (head_dim each).
+// Shape: NT = 3 query tiles, BKV = 48 keys per block (template parameters).  Round 2 also built and measured S
+// double-buffered with 2 x 64-key and 3 x 32-key blocks, and four tiles with 32-key blocks (all of TMEM): same outputs,
+// 11 - 24 % slower (fewer warps, or more hand-offs per key), so they are not in the tree (profiles/r2_notes.md).
+// TMEM columns: S[tile] (BKV each) | P[tile] (BKV/2 used, rounded to 16) | O[tile] (head_dim each).
 // Warps: 4 per tile softmax + epilogue (warp w owns TMEM lanes [32(w%4), +32)), then the TMA producer, then one MMA
 // issuer per tile (the first also allocates TMEM).
 #include "host_util.h"
@@ -61,8 +55,7 @@ constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softma
   } while (0)
 #endif
 
-// POLY: every POLY-th pair of exponentials on the FMA pipe (0: all on MUFU.EX2)
-template <int HD, int POLY, int NT, int BKV, int SST>
+template <int HD, int NT, int BKV>
 __global__ void __launch_bounds__(att_threads(NT), 1)
 attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
@@ -71,9 +64,8 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   static_assert(BKV == 32 || BKV == 48 || BKV == 64, "key block");
-  static_assert(SST == 1 || SST == 2, "S buffers per tile");
   constexpr int PSLOT = round16(BKV / 2);
-  constexpr int TM_S = 0, TM_P = NT * SST * BKV, TM_O = TM_P + NT * PSLOT;
+  constexpr int TM_S = 0, TM_P = NT * BKV, TM_O = TM_P + NT * PSLOT;
   static_assert(TM_O + NT * HD <= TMEM_COLS, "TMEM budget");
   constexpr int NQK = qk_nchunks(HD);
   constexpr int VW = v_w(HD);
@@ -84,13 +76,13 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   // Barriers first, at fixed offsets from the aligned base (the ring length is a run-time value: anything placed
   // behind it has an address the compiler re-derives from kernel parameters at every use once registers are short,
   // which put ~100 cycles of dependent latency in front of every barrier operation of the softmax warps).
-  // Per tile X, bars[TB X + k]: k = 0, 1 s_full[stage] (S_X of a block is in TMEM), 2, 3 s_free[stage] (it has been read
-  // into registers), 4 p_full (P_X(j) is in TMEM), 5 o_done (P.V_X(j) has retired: O updated, P buffer free), 6 first_s
-  // (tile X has issued its first S of the work item), 7 q_full (Q_X has landed), 8 q_empty (tile X's last S of the item
-  // is done).  Block g of a tile (counted across work items) uses S stage g % SST; its barriers' parity is (g / SST) & 1.
+  // Per tile X, bars[TB X + k]: k = 0 s_full (S_X(j) is in TMEM), 1 s_free (S_X(j) has been read into registers),
+  // 2 p_full (P_X(j) is in TMEM), 3 o_done (P.V_X(j) has retired: O updated, P buffer free), 4 first_s (tile X has
+  // issued its first S of the work item), 5 q_full (Q_X has landed), 6 q_empty (tile X's last S of the item is done).
+  // The parity of a barrier for block g of a tile (counted across work items) is g & 1.
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  constexpr int TB = 10;
-  constexpr int S_FULL = 0, S_FREE = 2, P_FULL = 4, O_DONE = 5, FIRST_S = 6, Q_FULL = 7, Q_EMPTY = 8;
+  constexpr int TB = 8;
+  constexpr int S_FULL = 0, S_FREE = 1, P_FULL = 2, O_DONE = 3, FIRST_S = 4, Q_FULL = 5, Q_EMPTY = 6;
   uint64_t* kv_full = bars + TB * NT;             // MAX_KV_STAGES
   uint64_t* kv_empty = kv_full + MAX_KV_STAGES;   // MAX_KV_STAGES
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + MAX_KV_STAGES);
@@ -116,10 +108,8 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       mbar_init(&kv_empty[i], NT);  // one commit per tile's MMA issuer
     }
     for (int i = 0; i < NT; ++i) {
-      for (int b = 0; b < 2; ++b) {
-        mbar_init(&bars[TB * i + S_FULL + b], 1);
-        mbar_init(&bars[TB * i + S_FREE + b], 4);
-      }
+      mbar_init(&bars[TB * i + S_FULL], 1);
+      mbar_init(&bars[TB * i + S_FREE], 4);
       mbar_init(&bars[TB * i + P_FULL], 4);
       mbar_init(&bars[TB * i + O_DONE], 1);
       mbar_init(&bars[TB * i + FIRST_S], 1);
@@ -231,10 +221,10 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     constexpr uint32_t idesc_o = make_idesc_bf16(BQ, HD, 0, 1);  // B = V is MN-major
     const uint32_t sq_lo = (smem_u32(sQ) & 0x3FFFF) >> 4;        // descriptor start-address fields (16-byte units)
     const uint32_t skv_lo = (smem_u32(sKV) & 0x3FFFF) >> 4;
-    auto issue_s = [&](int st, uint32_t g) {   // S_X(block g) = Q_X K^T for the K tile in stage st: HD/16 MMAs
+    auto issue_s = [&](int st) {   // S_X = Q_X K^T for the K tile in stage st: HD/16 MMAs
       const uint32_t q_lo = sq_lo + X * (q_tile_bytes >> 4) + (1u << 16);            // LBO field = 1 (unused)
       const uint32_t k_lo = skv_lo + st * (2 * kv_tile_bytes >> 4) + (1u << 16);
-      const uint32_t d_tmem = tmem_base + TM_S + (X * SST + (g % SST)) * BKV;
+      const uint32_t d_tmem = tmem_base + TM_S + X * BKV;
       bool first = true;
 #pragma unroll
       for (int c = 0; c < NQK; ++c) {
@@ -250,7 +240,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
           }
         }
       }
-      if (issuer) umma_commit(&bars[TB * X + S_FULL + (g % SST)]);
+      if (issuer) umma_commit(&bars[TB * X + S_FULL]);
     };
     // O_X += P_X V for the V tile in stage st.  V is MN-major: kv rows of 2*VW bytes, 8-row groups SBO = 16*VW
     // apart, the NV column chunks LBO = 2*BKV*VW apart.
@@ -266,19 +256,18 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       if (issuer) umma_commit(&bars[TB * X + O_DONE]);
     };
     // Two cursors walk the K/V ring, one block per step and across work items like the producer's: the stage whose
-    // K the next S reads (s_*) and the stage whose V the next P.V reads (pv_*); the S cursor runs SST blocks ahead.
+    // K the next S reads (s_*) and the stage whose V the next P.V reads (pv_*); the S cursor runs one block ahead.
     int s_st = 0, pv_st = 0;
     uint32_t s_ph = 0;
     uint32_t it = 0, gb = 0;   // items / key blocks of this tile finished so far (barrier phases run on across items)
     // S of block b of the current item (global block g = gb + b).  Waits for its K tile and for the softmax warps to
-    // have read the previous block that used the same S stage (g - SST; the first blocks of an item: the last ones of
-    // the previous item).
+    // have read the previous block's S (the first block of an item: the last one of the previous item).
     auto next_s = [&](int b, int nblk) {
       const uint32_t g = gb + b;
       mbar_wait(&kv_full[s_st], s_ph);
-      if (g >= (uint32_t)SST) mbar_wait(&bars[TB * X + S_FREE + (g % SST)], ((g / SST) - 1) & 1);
+      if (g >= 1) mbar_wait(&bars[TB * X + S_FREE], (g - 1) & 1);
       tc_fence_after();
-      issue_s(s_st, g);
+      issue_s(s_st);
       if (b + 1 == nblk && issuer) umma_commit(&bars[TB * X + Q_EMPTY]);   // this tile's last S of the item has been issued
       if (++s_st == KS) {
         s_st = 0;
@@ -306,11 +295,10 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       next_s(0, nblk);
       if (issuer) mbar_arrive(&bars[TB * X + FIRST_S]);
       if (lane == 0 && X == 0 && gb > 0) ATT_TRACE(0, (gb - 1) * 2);
-      if (SST == 2 && nblk > 1) next_s(1, nblk);
       for (int j = 0; j < nblk; ++j) {
-        // one S buffer: S(j+1) has to go out BEFORE this thread blocks on P(j), or the softmax warps would find no
-        // scores after their hand-off; two buffers: S(j+1) is out already and S(j+2) follows P.V(j)
-        if (SST == 1 && j + 1 < nblk) {
+        // S(j+1) has to go out BEFORE this thread blocks on P(j), or the softmax warps would find no scores after
+        // their hand-off
+        if (j + 1 < nblk) {
           next_s(j + 1, nblk);
           if (lane == 0 && X == 0) ATT_TRACE(0, (gb + j) * 2);
         }
@@ -321,7 +309,6 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         if (issuer) umma_commit(&kv_empty[pv_st]);   // K/V of block j: this tile's MMAs reading them have been issued
         __syncwarp();
         if (++pv_st == KS) pv_st = 0;
-        if (SST == 2 && j + 2 < nblk) next_s(j + 2, nblk);
       }
       gb += nblk;
       ++it;
@@ -331,24 +318,23 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
     const int X = warp >> 2;                     // query tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;        // row within the tile == TMEM lane
     const uint32_t t_lane = tmem_base + (uint32_t((warp & 3) * 32) << 16);
-    const uint32_t t_s0 = t_lane + TM_S + X * SST * BKV;   // S stage b of this tile: + b * BKV
+    const uint32_t t_s = t_lane + TM_S + X * BKV;
     const uint32_t t_p = t_lane + TM_P + X * PSLOT;
     constexpr int VB = BKV - 32;                           // columns beyond the first 32-column chunk: 0, 16 or 32
     const float c = p.scale_log2e;
     RowState<HD> rs;
     rs.t_o = t_lane + TM_O + X * HD;
     rs.o_done = &bars[TB * X + O_DONE];
-    auto signal_s_free = [&](uint32_t g) {
+    auto signal_s_free = [&]() {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[TB * X + S_FREE + (g % SST)]);
+      if (lane == 0) mbar_arrive(&bars[TB * X + S_FREE]);
     };
     uint32_t va[32], vb[VB > 0 ? VB : 1];
     // waits for S of block g (counted across items) and requests it from TMEM into va / vb
     auto request_s = [&](uint32_t g) {
-      mbar_wait(&bars[TB * X + S_FULL + (g % SST)], (g / SST) & 1);
+      mbar_wait(&bars[TB * X + S_FULL], g & 1);
       tc_fence_after();
-      const uint32_t t_s = t_s0 + (g % SST) * BKV;
       tmem_ld32(t_s, va);
       if constexpr (VB == 16) tmem_ld16(t_s + 32, reinterpret_cast<uint32_t(&)[16]>(vb));
       if constexpr (VB == 32) tmem_ld32(t_s + 32, reinterpret_cast<uint32_t(&)[32]>(vb));
@@ -392,7 +378,7 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         tmem_ld_wait_on(va);
         if constexpr (VB == 16) tmem_ld_wait_on16(reinterpret_cast<uint32_t(&)[16]>(vb));
         if constexpr (VB == 32) tmem_ld_wait_on(reinterpret_cast<uint32_t(&)[32]>(vb));
-        signal_s_free(gb + j);
+        signal_s_free();
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 1);
         // Exponential phases in RELAY.  Left alone, the NT softmax warps that share an SM sub-partition fall into
         // lock-step: they queue at the MUFU pipe together (24 cycles per column for three warps, the pipe's limit) and
@@ -407,23 +393,23 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         const uint32_t g_blk = gb + j;
         if (p.relay > 0 && (X > 0 || g_blk > 0)) named_bar_sync(1 + (X + NT - 1) % NT, 256);
         if (ncols == BKV) {
-          softmax_chunk<HD, 0, 16, false, BKV / 2, POLY>(va, ncols, c, rs, pk);
+          softmax_chunk<HD, 0, 16, false, BKV / 2>(va, ncols, c, rs, pk);
           if (p.relay == 1) named_bar_arrive(1 + X, 256);
-          softmax_chunk<HD, 16, 16, false, BKV / 2, POLY>(va + 16, ncols, c, rs, pk);
+          softmax_chunk<HD, 16, 16, false, BKV / 2>(va + 16, ncols, c, rs, pk);
           if (p.relay >= 2) named_bar_arrive(1 + X, 256);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, false, BKV / 2, POLY>(vb, ncols, c, rs, pk);
+          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, false, BKV / 2>(vb, ncols, c, rs, pk);
         } else {
-          softmax_chunk<HD, 0, 16, true, BKV / 2, POLY>(va, ncols, c, rs, pk);
+          softmax_chunk<HD, 0, 16, true, BKV / 2>(va, ncols, c, rs, pk);
           if (p.relay == 1) named_bar_arrive(1 + X, 256);
-          softmax_chunk<HD, 16, 16, true, BKV / 2, POLY>(va + 16, ncols, c, rs, pk);
+          softmax_chunk<HD, 16, 16, true, BKV / 2>(va + 16, ncols, c, rs, pk);
           if (p.relay >= 2) named_bar_arrive(1 + X, 256);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, true, BKV / 2, POLY>(vb, ncols, c, rs, pk);
+          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, true, BKV / 2>(vb, ncols, c, rs, pk);
         }
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 4);
-        // One S buffer: S(j+1) was issued when s_free(j) arrived.  Two: it was issued a whole block ago.  Either way
-        // its chunks are requested now so that the TMEM read latency hides under the P hand-off below.
+        // S(j+1) was issued when s_free(j) arrived, i.e. long ago: its chunks are requested now so that the TMEM read
+        // latency hides under the P hand-off below
         if (j + 1 < nblk) {
           request_s(gb + j + 1);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 3);
@@ -432,13 +418,11 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
           const float2 t = fadd2(rs.sm[0], rs.sm[1]);
           rs.sum += t.x + t.y;
         }
-        // The P buffer is free once P.V_X(j-1) has retired.  One S buffer: S_X(j+1) was issued after P.V_X(j-1) by the
-        // same thread and tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it and
-        // only the last block has to ask o_done (an mbarrier round trip costs ~100 cycles on this critical path).  Two S
-        // buffers: S_X(j+1) went out BEFORE P.V_X(j-1), so o_done is asked every time - P.V_X(j-1) was issued one
-        // exponential phase ago and has normally retired.  Block 0 of a later item: the epilogue below has waited for
-        // the previous item's last P.V.
-        if (j > 0 && (SST == 2 || j + 1 >= nblk)) {
+        // The P buffer is free once P.V_X(j-1) has retired.  S_X(j+1) was issued after P.V_X(j-1) by the same thread
+        // and tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it; only the
+        // last block has to ask o_done (an mbarrier round trip costs ~100 cycles on this critical path).  Block 0 of
+        // a later item: the epilogue below has waited for the previous item's last P.V.
+        if (j > 0 && j + 1 >= nblk) {
           mbar_wait(&bars[TB * X + O_DONE], (gb + j - 1) & 1);
           tc_fence_after();
         }
@@ -538,15 +522,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "attention: buffers must be 16-byte aligned");
   const int d = H * hd;
-  // OASR_ATT_CFG = <tiles><keys per block> of the instantiated shapes: 348 (three tiles, 48-key blocks, one S buffer:
-  // round 1's shape), 264 (two tiles, 64-key blocks, two S buffers) or 332 (three tiles, 32-key blocks, two S
-  // buffers; tests/test_gpu_kernels.py::test_attention_shapes_agree).
-  static const int cfg_env = [] {
-    const char* e = std::getenv("OASR_ATT_CFG");
-    return e != nullptr ? std::atoi(e) : 348;
-  }();
-  const int cfg = (cfg_env == 348 || cfg_env == 264 || cfg_env == 332) ? cfg_env : 348;
-  const int NT = cfg / 100, bkv = cfg % 100;
+  constexpr int NT = 3, bkv = 48;   // the measured best of the shapes TMEM allows (see the file header)
   AttMaps m;
   {
     std::lock_guard<std::mutex> g(g_att7_mu);
@@ -606,32 +582,17 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   const int num_sms = device_sm_count();
   dim3 grid(p.n_items < num_sms ? p.n_items : num_sms);   // persistent: one CTA per SM
   cudaError_t attr_err = cudaSuccess;
-  // OASR_ATT_POLY = 3: every third pair of exponentials on the FMA pipe (default 0: all on MUFU.EX2; measured slower
-  // in every shape so far, profiles/r2_notes.md; tests/test_gpu_kernels.py::test_attention_poly_settings_agree)
-  static const int poly_env = [] {
-    const char* e = std::getenv("OASR_ATT_POLY");
-    return e != nullptr ? std::atoi(e) : 0;
-  }();
-  const int poly = poly_env == 3 ? 3 : 0;
-#define OASR_ATT_LAUNCH(HDV, PV, NTV, BKVV, SSTV)                                                                      \
-  {                                                                                                                    \
-    static unsigned long long attr_mask = 0;                                                                           \
-    if (first_use_on_this_device(&attr_mask))                                                                          \
-      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV, PV, NTV, BKVV, SSTV>,                                   \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);                        \
-    if (attr_err == cudaSuccess)                                                                                       \
-      attention_v7_kernel<HDV, PV, NTV, BKVV, SSTV><<<grid, att_threads(NTV), smem_bytes, stream>>>(                   \
-          m.tm[0], m.tm[1], m.tm[2], m.tm[3], m.tm[4], m.tm[5], m.tm[6], p);                                           \
+#define OASR_ATT_CASE(HDV)                                                                                            \
+  case HDV: {                                                                                                         \
+    static unsigned long long attr_mask = 0;                                                                          \
+    if (first_use_on_this_device(&attr_mask))                                                                         \
+      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV, NT, bkv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      227 * 1024);                                                                    \
+    if (attr_err == cudaSuccess)                                                                                      \
+      attention_v7_kernel<HDV, NT, bkv><<<grid, att_threads(NT), smem_bytes, stream>>>(                               \
+          m.tm[0], m.tm[1], m.tm[2], m.tm[3], m.tm[4], m.tm[5], m.tm[6], p);                                          \
+    break;                                                                                                            \
   }
-#define OASR_ATT_SHAPES(HDV, PV)                                  \
-  if (cfg == 264) OASR_ATT_LAUNCH(HDV, PV, 2, 64, 2)              \
-  else if (cfg == 332) OASR_ATT_LAUNCH(HDV, PV, 3, 32, 2)         \
-  else OASR_ATT_LAUNCH(HDV, PV, 3, 48, 1)
-#define OASR_ATT_CASE(HDV)                       \
-  case HDV:                                      \
-    if (poly == 3) { OASR_ATT_SHAPES(HDV, 3) }   \
-    else { OASR_ATT_SHAPES(HDV, 0) }             \
-    break;
   switch (hd) {
     OASR_ATT_CASE(16)
     OASR_ATT_CASE(32)
@@ -641,8 +602,6 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
     default: return fail(OASR_ERR_UNSUPPORTED, "attention v7: head_dim must be a multiple of 16 in [16, 80]");
   }
 #undef OASR_ATT_CASE
-#undef OASR_ATT_SHAPES
-#undef OASR_ATT_LAUNCH
   OASR_CUDA_CHECK(attr_err);
   OASR_CUDA_CHECK(cudaGetLastError());
   if (p.trace != nullptr) {
