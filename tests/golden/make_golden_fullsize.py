@@ -15,6 +15,9 @@ asserts oracle(fp32) == HF(fp32) to fp32 round-off at full width, full depth and
   oracle_3b_window.npz  omniASR_CTC_3B (d 2048, 60 layers, head_dim 128), window 0 of the same batch: the same fields.
                         Read by tests/test_gpu_engine.py::test_config3_3b_full_depth_window.
 
+  oracle_7b_window.npz  omniASR_CTC_7B (128 layers), the same window, oracle only (`7b` on the command line; the GPU test that
+                        reads it is opt-in, OASR_TEST_7B=1: 26 GB of host weights).
+
   oracle_300m_gettysburg_emu.npz
                         BASELINE configs[0] (omniASR_CTC_300M on the committed 16 kHz gettysburg fixture): ids and margins
                         in BOTH oracle modes plus the HF ids (oracle_300m_gettysburg.npz holds the fp32 ids only).
@@ -73,7 +76,7 @@ def pack(prefix, o, b, rows):
     }
 
 
-def run(model: str, indices, ns, out_name: str, hf_window: int = 0, wave=None):
+def run(model: str, indices, ns, out_name: str, hf_window: int = 0, wave=None, with_hf: bool = True):
     t0 = time.time()
     cfg = O.PRESETS[model]
     w = O.init_weights(cfg, seed=0)
@@ -96,6 +99,13 @@ def run(model: str, indices, ns, out_name: str, hf_window: int = 0, wave=None):
         rows = np.arange(0, f32.n_frames[b], ROW_STEP)
         for k, v in {**pack(f"w{b}_f32", f32, b, rows), **pack(f"w{b}_emu", emu, b, rows)}.items():
             fields[k] = v
+    if not with_hf:     # 7B: the oracle alone (a second 26 GB model does not fit beside it in this container)
+        fields["hf_window"] = -1
+        np.savez_compressed(OUT / out_name, **fields)
+        print(f"{model}: oracle vectors written (no HF run), emu/f32 id agreement w0 "
+              f"{float((fields['w0_emu_ids'] == fields['w0_f32_ids']).mean()):.4f}; {(OUT / out_name).stat().st_size} bytes, "
+              f"{time.time() - t0:.0f} s", flush=True)
+        return
     # ---- the independent implementation at full size (one window: its cost is the oracle's)
     b = hf_window
     nf = f32.n_frames[b]
@@ -133,3 +143,5 @@ if __name__ == "__main__":
         run("omniASR_CTC_300M", (0,), [g.shape[1]], "oracle_300m_gettysburg_emu.npz", wave=g)
     if "3b" in which:
         run("omniASR_CTC_3B", (0,), [L], "oracle_3b_window.npz")
+    if "7b" in which:      # not in the default list: 26 GB of fp32 weights, ~6 min
+        run("omniASR_CTC_7B", (0,), [L], "oracle_7b_window.npz", with_hf=False)

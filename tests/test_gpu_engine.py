@@ -300,6 +300,30 @@ def test_config3_3b_full_depth_window(device):
     eng.close()
 
 
+def test_config4_7b_full_depth_window(device):
+    """omniASR_CTC_7B at its real depth (128 layers, d 2048: BASELINE configs[3]'s model) on one GPU, one 30 s window,
+    against the committed oracle vectors.  Opt-in (OASR_TEST_7B=1): the test builds 26 GB of fp32 weights on the host
+    with the oracle's generator, which takes minutes; the builder's run is recorded in profiles/r2_parity_7b.txt."""
+    import os
+    if os.environ.get("OASR_TEST_7B") != "1":
+        pytest.skip("set OASR_TEST_7B=1 (26 GB of host weights, several minutes)")
+    import bench
+    from tests.golden.make_golden_fullsize import BENCH_SEED, ROW_STEP
+    g = np.load(GOLDEN / "oracle_7b_window.npz")
+    wave = bench.synthetic_windows(32, BENCH_SEED)
+    assert hashlib.sha256(wave.numpy().tobytes()).hexdigest() == str(g["bench_batch_sha256"])
+    wave = wave[:1].contiguous()
+    eng = CtcEngine(get_model_config("omniASR_CTC_7B"), device=device)
+    w = O.init_weights(O.PRESETS["omniASR_CTC_7B"], seed=0)
+    eng.load_state_dict(w)
+    del w
+    res = eng.forward(wave.to(device), [wave.shape[1]], normalised=False, return_hidden=True)
+    assert res.n_frames == [1499]
+    rows = torch.arange(0, 1499, ROW_STEP)
+    _check_fullsize_window("7B", res.frame_ids[0, :1499], res.hidden[0].cpu()[rows], g, 0)
+    eng.close()
+
+
 def test_batch_invariance_and_determinism_full_window(device):
     """Size-independent properties at the real window size (30 s, T = 1499) on the 1B architecture with few
     layers: a window's ids do not depend on its batch neighbours, nor on the run."""
