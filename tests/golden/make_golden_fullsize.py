@@ -15,8 +15,8 @@ asserts oracle(fp32) == HF(fp32) to fp32 round-off at full width, full depth and
   oracle_3b_window.npz  omniASR_CTC_3B (d 2048, 60 layers, head_dim 128), window 0 of the same batch: the same fields.
                         Read by tests/test_gpu_engine.py::test_config3_3b_full_depth_window.
 
-  oracle_7b_window.npz  omniASR_CTC_7B (128 layers), the same window, oracle only (`7b` on the command line; the GPU test that
-                        reads it is opt-in, OASR_TEST_7B=1: 26 GB of host weights).
+  oracle_7b_window.npz  omniASR_CTC_7B (128 layers), the same window, oracle only (`7b` on the command line: 26 GB of fp32
+                        weights, no room for a second model).  Read by test_config4_7b_full_depth_window.
 
   oracle_300m_gettysburg_emu.npz
                         BASELINE configs[0] (omniASR_CTC_300M on the committed 16 kHz gettysburg fixture): ids and margins

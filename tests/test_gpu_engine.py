@@ -302,11 +302,7 @@ def test_config3_3b_full_depth_window(device):
 
 def test_config4_7b_full_depth_window(device):
     """omniASR_CTC_7B at its real depth (128 layers, d 2048: BASELINE configs[3]'s model) on one GPU, one 30 s window,
-    against the committed oracle vectors.  Opt-in (OASR_TEST_7B=1): the test builds 26 GB of fp32 weights on the host
-    with the oracle's generator, which takes minutes; the builder's run is recorded in profiles/r2_parity_7b.txt."""
-    import os
-    if os.environ.get("OASR_TEST_7B") != "1":
-        pytest.skip("set OASR_TEST_7B=1 (26 GB of host weights, several minutes)")
+    against the committed oracle vectors (26 GB of fp32 weights built on the host with the oracle's generator: ~40 s)."""
     import bench
     from tests.golden.make_golden_fullsize import BENCH_SEED, ROW_STEP
     g = np.load(GOLDEN / "oracle_7b_window.npz")
