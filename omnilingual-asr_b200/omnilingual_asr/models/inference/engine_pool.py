@@ -217,6 +217,21 @@ class EnginePool:
         for req in finished:
             req.done.set()
 
+    def _deliver_empty(self, engine: Any, jobs: List[Tuple[_Request, int]]) -> None:
+        finished: List[_Request] = []
+        for req, i in jobs:
+            s0, n = req.windows[i]
+            tok = WindowTokens(i, s0, n, 0, np.zeros((0,), np.int32), np.zeros((0,), np.int32))
+            extra = req.post(tok) if req.post is not None else None
+            with self._cv:
+                req.results[i] = tok
+                req.extras[i] = extra
+                req.remaining -= 1
+                if req.remaining == 0:
+                    finished.append(req)
+        for req in finished:
+            req.done.set()
+
     def _fail(self, jobs: List[Tuple[_Request, int]], err: BaseException) -> None:
         for req in {id(r): r for r, _ in jobs}.values():
             with self._cv:
@@ -247,6 +262,14 @@ class EnginePool:
                     L = max(req.windows[i][1] for req, i in jobs)
                     B = len(jobs)
                     dtype = jobs[0][0].dtype
+                    if int(engine.cfg.feature_length(int(L))) == 0:
+                        # nothing in this batch reaches one frame (empty recording, a stub shorter than the feature
+                        # extractor's 400-sample receptive field): no tokens, and no device step to find that out
+                        self._deliver_empty(engine, jobs)
+                        with self._cv:
+                            self._inflight[k] -= len(jobs)
+                            self._cv.notify_all()
+                        continue
                     T = max(int(engine.cfg.feature_length(int(L))), 1)
                     buf = st.wave.get(dtype)
                     if buf is None or buf.size < B * L:

@@ -604,3 +604,52 @@ def test_graph_switch_off_gives_the_same_ids(device, tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(np.load(out))
     assert (outs[0] == outs[1]).all()
+
+
+def test_edge_windows_empty_sub_frame_and_maximum_length(device):
+    """Edge cases of the path on the device: an empty recording and a stub below the 400-sample receptive field give no
+    segments; a batch mixing full windows with a frame-less one leaves the full ones untouched; the longest window the
+    boundary accepts (40 s = 640 000 samples = 1999 frames, MAX_ALLOWED_AUDIO_SEC) agrees with the oracle."""
+    from omnilingual_asr.models.inference.ctc_pipeline import CTCASRPipeline
+    ocfg, w, eng = make_engine("tiny", device)
+    pipe = CTCASRPipeline(eng.cfg, engine=eng, window_seconds=1.0, batch_windows=4, distributed=False)
+    rng = np.random.default_rng(5)
+    assert pipe.transcribe_chunked(np.zeros((0,), np.float32), sample_rate=16000).segments == []
+    assert pipe.transcribe_chunked((rng.standard_normal(399) * 0.1).astype(np.float32), sample_rate=16000).segments == []
+    x = (rng.standard_normal(32000 + 120) * 0.2).astype(np.float32)
+    a = pipe.transcribe_chunked(x, sample_rate=16000)
+    b = pipe.transcribe_chunked(x[:32000], sample_rate=16000)
+    assert [(s.start, s.end, s.text) for s in a.segments] == [(s.start, s.end, s.text) for s in b.segments] and a.segments
+    # maximum length, ragged beside a short window
+    L = 640_000
+    g = torch.Generator().manual_seed(9)
+    wave = torch.randn(2, L, generator=g)
+    ns = [L, 123_457]
+    wave[1, ns[1]:] = 0
+    res = eng.forward(wave.to(device), ns, normalised=False)
+    assert res.n_frames == [1999, O.feature_length(ns[1])]
+    emu = O.forward(w, O.wave_layer_norm(wave, ns), ns, ocfg, emulate_bf16=True, return_logits=True)
+    _, a_m, excl = agreement(res.frame_ids, emu, NEAR_TIE)
+    assert a_m == 1.0
+    for bb, nf in enumerate(emu.n_frames):
+        assert (res.frame_ids[bb, nf:] == 0).all()
+    pipe.close()
+    eng.close()
+
+
+def test_async_api_misuse_is_reported_not_fatal(device):
+    ocfg, w, eng = make_engine("tiny", device)
+    with pytest.raises(ValueError):
+        eng.wait(5)                                   # no such ticket
+    x = torch.zeros((2, 8000), dtype=torch.float32, pin_memory=True).numpy()
+    T = eng.feature_length(8000)
+    ids = torch.zeros((2, T), dtype=torch.int32, pin_memory=True).numpy()
+    with pytest.raises(ValueError):
+        eng.submit_host(x, [8000], ids, ids.copy(), np.zeros(2, np.int32))          # one length for two windows
+    with pytest.raises(ValueError):
+        eng.submit_host(x, [8000, 8000], ids[:, :T - 1].copy(), ids.copy(), np.zeros(2, np.int32))   # wrong output shape
+    t = eng.submit_host(x, [8000, 8000], ids, ids.copy(), torch.zeros(2, dtype=torch.int32, pin_memory=True).numpy())
+    eng.wait(t)
+    res = eng.transcribe_host(x, [8000, 8000])        # the synchronous call still works afterwards
+    assert len(res.token_ids) == 2
+    eng.close()

@@ -403,3 +403,38 @@ def test_pool_failure_reaches_the_caller_and_the_pool_lives_on():
     pipe.close()
     with pytest.raises(RuntimeError):
         pipe.transcribe_chunked(x, sample_rate=16000)                            # a closed pool refuses work
+
+
+def test_empty_and_sub_frame_audio_give_no_segments(engine):
+    """Edge cases of the boundary: an empty recording is one empty window (the reference's chunker always yields at
+    least one chunk, gemini_pipeline.py:243-310), and audio shorter than the feature extractor's receptive field (400
+    samples) has no frame at all: both return no segments instead of failing."""
+    pipe = CTCASRPipeline(engine.cfg, engine=engine, window_seconds=1.0, batch_windows=4, distributed=False)
+    for x in (np.zeros((0,), np.float32), noise(399 / 16000.0, seed=1)[:399], np.zeros((100,), np.int16)):
+        res = pipe.transcribe_chunked(x, sample_rate=16000)
+        assert res.segments == []
+    # a recording whose LAST window is below one frame: the full windows are transcribed, the stub adds nothing
+    x = noise(2.0, seed=2)
+    x = np.concatenate([x, np.zeros((120,), np.float32)])
+    a = pipe.transcribe_chunked(x, sample_rate=16000)
+    b = pipe.transcribe_chunked(x[:32000], sample_rate=16000)
+    assert _texts(a) == _texts(b) and len(a.segments) > 0
+    pipe.close()
+
+
+def test_pool_run_clips_keeps_input_order_and_mixes_sample_types():
+    """ASRInferencePipeline's path: independent clips of different lengths (and PCM16 beside float32) come back in
+    input order, each equal to its own single-clip result."""
+    from omnilingual_asr.models.inference.engine_pool import EnginePool
+    from tests._fake_engine import OracleEngine
+    eng = OracleEngine("tiny")
+    pool = EnginePool([eng], batch_windows=3)
+    clips = [noise(0.3 + 0.11 * i, seed=60 + i) for i in range(5)]
+    clips[2] = (clips[2] * 20000).astype(np.int16)
+    got = pool.run_clips(clips)
+    assert [t.index for t in got] == list(range(5))
+    for c, t in zip(clips, got):
+        alone = pool.run_clips([c])[0]
+        assert t.token_ids.tolist() == alone.token_ids.tolist() and t.n_samples == len(c)
+    assert pool.run_clips([]) == []
+    pool.close()
