@@ -785,8 +785,31 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
 
 // CTA pairs whenever a tile spans full 256-column MMAs (every encoder / FE / CTC GEMM), single CTAs for narrower outputs
 // (pos-conv groups, the small test shapes)
+// A single 30 s window (M = 1499) gives the encoder GEMMs too few 256 x 256 pair tiles for 74 CTA pairs: out-proj and FFN2
+// 30 tiles (41 % of the SMs busy), QKV 90 (two waves, the second a quarter full).  When the pair tiling fills less
+// than ~two waves and 128 x 128 single-CTA tiles fill their waves better, the small tiles run instead (81 % for all four
+// encoder shapes at M = 1499); the epilogues are the same code at BN = 128.
+template <int EPI>
+constexpr bool has_small_tile() { return EPI == EPI_BF16 || EPI == EPI_BF16_GELU || EPI == EPI_F32_RESID; }
+
+inline bool prefer_small_tiles(const GemmArgs& a) {
+  if (a.N < 256 || a.taps != 1 || a.groups != 1) return false;
+  const long long sms = device_sm_count();
+  const long long mp = (a.rows_per_batch + 255) / 256, np = (a.N + 255) / 256;
+  const long long ms = (a.rows_per_batch + 127) / 128, ns = (a.N + 127) / 128;
+  const long long tp = mp * np * a.batches, ts = ms * ns * a.batches;
+  const long long pairs = sms / 2;
+  if (tp > 2 * pairs) return false;
+  const double eff_p = (double)tp / (double)(((tp + pairs - 1) / pairs) * pairs);
+  const double eff_s = (double)ts / (double)(((ts + sms - 1) / sms) * sms);
+  return eff_s > 1.15 * eff_p;
+}
+
 template <int BN, int EPI>
 int launch(const GemmArgs& a, cudaStream_t stream) {
+  if constexpr (BN == 256 && has_small_tile<EPI>()) {
+    if (prefer_small_tiles(a)) return launch_cg<128, EPI, 1>(a, stream);
+  }
   if (BN >= 256 && a.N >= BN) return launch_cg<BN, EPI, 2>(a, stream);
   return launch_cg<BN, EPI, 1>(a, stream);
 }
