@@ -25,7 +25,12 @@ using namespace att;
 constexpr int BQ = 128;
 __host__ __device__ constexpr int att_threads(int nt) { return (nt * 4 + 1 + nt) * 32; }
 constexpr int MAX_KV_STAGES = 8;
-constexpr int TMEM_COLS = 512;
+// TMEM columns a CTA allocates: a power of two covering S + P + O of its NT tiles (one tile: 256, so that two such CTAs
+// share an SM; three tiles: all 512)
+__host__ __device__ constexpr int att_tmem_cols(int nt, int bkv, int hd) {
+  const int need = nt * bkv + nt * ((bkv / 2 + 15) & ~15) + nt * hd;
+  return need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+}
 constexpr int KV_PREFETCH = 4;             // K/V blocks of the next work item requested before its Q
 constexpr int START_OFFSET_CYCLES = 450;   // tile X issues its first S this many cycles after tile X-1
 
@@ -56,7 +61,7 @@ constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softma
 #endif
 
 template <int HD, int NT, int BKV>
-__global__ void __launch_bounds__(att_threads(NT), 1)
+__global__ void __launch_bounds__(att_threads(NT), NT == 1 ? 2 : 1)
 attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_constant__ CUtensorMap tmq32,
                     const __grid_constant__ CUtensorMap tmq16, const __grid_constant__ CUtensorMap tmk64,
                     const __grid_constant__ CUtensorMap tmk32, const __grid_constant__ CUtensorMap tmk16,
@@ -66,7 +71,8 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
   static_assert(BKV == 32 || BKV == 48 || BKV == 64, "key block");
   constexpr int PSLOT = round16(BKV / 2);
   constexpr int TM_S = 0, TM_P = NT * BKV, TM_O = TM_P + NT * PSLOT;
-  static_assert(TM_O + NT * HD <= TMEM_COLS, "TMEM budget");
+  constexpr int TMEM_COLS = att_tmem_cols(NT, BKV, HD);
+  static_assert(TM_O + NT * HD <= TMEM_COLS && TMEM_COLS <= 512, "TMEM budget");
   constexpr int NQK = qk_nchunks(HD);
   constexpr int VW = v_w(HD);
   constexpr int NV = HD / VW;
@@ -522,7 +528,12 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   OASR_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "attention: buffers must be 16-byte aligned");
   const int d = H * hd;
-  constexpr int NT = 3, bkv = 48;   // the measured best of the shapes TMEM allows (see the file header)
+  constexpr int bkv = 48;   // three tiles x 48-key blocks: the measured best of the shapes TMEM allows (file header)
+  // A single window does not give the three-tile shape enough work items for one CTA per SM (1B, one 30 s window: 4 query
+  // triples x 16 heads = 64 items for 148 SMs, 42 us per launch).  Then every CTA takes ONE tile - 192 threads, 256 TMEM
+  // columns, a short K/V ring - so that two CTAs share an SM and 192 items run in one wave.
+  const int items3 = ((T + 3 * BQ - 1) / (3 * BQ)) * H * B;
+  const int NT = items3 < device_sm_count() ? 1 : 3;
   AttMaps m;
   {
     std::lock_guard<std::mutex> g(g_att7_mu);
@@ -555,6 +566,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   const int q_tile_bytes = BQ * hd * 2, kv_tile_bytes = bkv * hd * 2;
   int kv_stages = (227 * 1024 - 2048 - 2 * NT * q_tile_bytes) / (2 * kv_tile_bytes);   // Q tiles + output staging of the same size
   kv_stages = kv_stages > MAX_KV_STAGES ? MAX_KV_STAGES : kv_stages;
+  if (NT == 1 && kv_stages > 4) kv_stages = 4;   // two CTAs per SM: 2 x (Q + staging + 4 K/V stages) fits 227 KB up to head_dim 80
   OASR_REQUIRE(kv_stages >= 3, "attention: tile does not fit shared memory");
   p.kv_stages = kv_stages;
   const int smem_bytes = 2 * NT * q_tile_bytes + 2 * kv_tile_bytes * kv_stages + 1024 + 1024;
@@ -570,7 +582,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
     const char* e = std::getenv("OASR_ATT_RELAY");   // 0: free-running tiles; 1 / 2: hand on after 16 / 32 columns
     return e != nullptr ? std::atoi(e) : 1;
   }();
-  p.relay = relay < 0 ? 0 : (relay > 2 ? 2 : relay);
+  p.relay = NT == 1 ? 0 : (relay < 0 ? 0 : (relay > 2 ? 2 : relay));   // one tile: nobody to take turns with
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
   if (trace_path != nullptr) {
     OASR_CUDA_CHECK(cudaMalloc(&p.trace, 5 * TRACE_EVENTS * sizeof(long long)));
@@ -579,20 +591,24 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   p.n_qt = (T + NT * BQ - 1) / (NT * BQ);
   OASR_REQUIRE((long long)p.n_qt * H * B < (1ll << 31), "attention: too many work items");
   p.n_items = p.n_qt * H * B;
-  const int num_sms = device_sm_count();
-  dim3 grid(p.n_items < num_sms ? p.n_items : num_sms);   // persistent: one CTA per SM
+  const int slots = device_sm_count() * (NT == 1 ? 2 : 1);   // persistent: one CTA per SM (two of the one-tile shape)
+  dim3 grid(p.n_items < slots ? p.n_items : slots);
   cudaError_t attr_err = cudaSuccess;
-#define OASR_ATT_CASE(HDV)                                                                                            \
-  case HDV: {                                                                                                         \
-    static unsigned long long attr_mask = 0;                                                                          \
-    if (first_use_on_this_device(&attr_mask))                                                                         \
-      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV, NT, bkv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      227 * 1024);                                                                    \
-    if (attr_err == cudaSuccess)                                                                                      \
-      attention_v7_kernel<HDV, NT, bkv><<<grid, att_threads(NT), smem_bytes, stream>>>(                               \
-          m.tm[0], m.tm[1], m.tm[2], m.tm[3], m.tm[4], m.tm[5], m.tm[6], p);                                          \
-    break;                                                                                                            \
+#define OASR_ATT_LAUNCH(HDV, NTV)                                                                                      \
+  {                                                                                                                    \
+    static unsigned long long attr_mask = 0;                                                                           \
+    if (first_use_on_this_device(&attr_mask))                                                                          \
+      attr_err = cudaFuncSetAttribute(attention_v7_kernel<HDV, NTV, bkv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      227 * 1024);                                                                     \
+    if (attr_err == cudaSuccess)                                                                                       \
+      attention_v7_kernel<HDV, NTV, bkv><<<grid, att_threads(NTV), smem_bytes, stream>>>(                              \
+          m.tm[0], m.tm[1], m.tm[2], m.tm[3], m.tm[4], m.tm[5], m.tm[6], p);                                           \
   }
+#define OASR_ATT_CASE(HDV)                  \
+  case HDV:                                 \
+    if (NT == 1) OASR_ATT_LAUNCH(HDV, 1)    \
+    else OASR_ATT_LAUNCH(HDV, 3)            \
+    break;
   switch (hd) {
     OASR_ATT_CASE(16)
     OASR_ATT_CASE(32)
@@ -602,6 +618,7 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
     default: return fail(OASR_ERR_UNSUPPORTED, "attention v7: head_dim must be a multiple of 16 in [16, 80]");
   }
 #undef OASR_ATT_CASE
+#undef OASR_ATT_LAUNCH
   OASR_CUDA_CHECK(attr_err);
   OASR_CUDA_CHECK(cudaGetLastError());
   if (p.trace != nullptr) {

@@ -208,7 +208,9 @@ def test_posconv(device, gen, d, groups, k, T, B):
 @pytest.mark.parametrize("H,hd,T,B,ragged", [(4, 64, 300, 2, False), (4, 80, 300, 2, True), (2, 128, 257, 2, True),
                                              (16, 80, 1499, 1, False), (3, 16, 100, 1, False),
                                              (2, 96, 400, 2, True), (2, 112, 333, 2, True), (2, 128, 1499, 1, False),
-                                             (2, 32, 129, 1, False), (2, 48, 515, 2, True)])
+                                             (2, 32, 129, 1, False), (2, 48, 515, 2, True),
+                                             # >= 148 work items: the three-tile persistent shape (fewer: one tile per CTA)
+                                             (16, 80, 500, 5, True), (16, 64, 400, 10, True)])
 def test_attention(device, gen, H, hd, T, B, ragged):
     d = H * hd
     qkv = _rand((B * T, 3 * d), gen).bfloat16()
