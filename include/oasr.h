@@ -93,20 +93,26 @@ OASR_API int oasr_finalize_weights(OasrHandle h);
 /* ---- tensor parallelism (7B encoder, BASELINE config 4; upstream has no counterpart: a replica per GPU is the
  * default and needs none of this) --------------------------------------------------------------------------
  * The encoder layers are split Megatron-style over `world` ranks, one process and one handle per GPU: q/k/v and
- * FFN1 by output columns (whole heads), out-proj and FFN2 by input columns; their partial outputs are summed with
- * one all-reduce each (NCCL over NVLink, loaded with dlopen) and added to the fp32 residual stream inside the next
- * LayerNorm pass.  Every rank loads the FULL weights with oasr_load_weight and keeps its slice at finalize.
+ * FFN1 by output columns (whole heads), out-proj and FFN2 by input columns.  Every rank loads the FULL weights with
+ * oasr_load_weight and keeps its slice at finalize.  Two ways to sum the partial outputs of out-proj / FFN2:
+ *   nccl   one ncclAllReduce (fp32; NCCL loaded with dlopen) followed by one add + LayerNorm pass;
+ *   peer   (after oasr_tp_ipc_export / _import) PUSH-based over NVLink peer memory: the GEMM epilogue writes each
+ *          partial row, rounded to bf16, into the receive region of the rank that owns the row; the owner adds the
+ *          `world` partial rows to its slice of the fp32 residual stream in rank order, applies LayerNorm and stores the
+ *          bf16 row into every rank's buffer; flags in peer memory order the two steps.
  * oasr_tp_unique_id: rank 0 obtains the 128-byte NCCL id, the host broadcasts it.
  * oasr_tp_init: collective; call after oasr_create and before oasr_finalize_weights.
- * oasr_tp_emulate: one handle computes all `world` shards in turn and sums them locally (no communicator) - the
- * single-GPU parity check of the slicing. */
+ * oasr_tp_emulate: one handle computes all `world` shards in turn and reduces them locally with the peer path's
+ * kernel (no communicator) - the single-GPU parity check of the slicing and of the rounding points.
+ * All ranks must call the forward with the SAME batch, in the same order, together: a rank that waits longer than
+ * OASR_TP_TIMEOUT_MS (default 60 000) for a peer's flag gives up, and this and every later call on the handle returns
+ * OASR_ERR_STATE (nothing traps; rebuild the group's engines). */
 OASR_API int oasr_tp_unique_id(void* id_out_128_bytes);
 OASR_API int oasr_tp_init(OasrHandle h, int32_t rank, int32_t world, const void* id_128_bytes);
 OASR_API int oasr_tp_emulate(OasrHandle h, int32_t world);
-/* Peer-memory path (optional, after oasr_tp_init and before the first forward): the all-reduce, the residual add
- * and the LayerNorm of every row-parallel GEMM run as ONE kernel that reads the peers' partial sums and writes x and
- * LN(x) into every rank's buffers over NVLink (CUDA IPC mappings), instead of ncclAllReduce + a LayerNorm pass.
- * export: allocates this rank's arena for batches up to (B, L) and returns its 64-byte cudaIpcMemHandle_t;
+/* Peer-memory path (after oasr_tp_init and before the first forward):
+ * export: allocates this rank's arena (residual stream, LayerNorm rows, receive region, flags) for batches up to
+ *         (B, L) and returns its 64-byte cudaIpcMemHandle_t;
  * import: takes the `world` handles in rank order (the host all-gathers them) and maps the peers. */
 OASR_API int oasr_tp_ipc_export(OasrHandle h, int32_t B, int32_t L, void* handle_out_64_bytes);
 OASR_API int oasr_tp_ipc_import(OasrHandle h, const void* handles_world_x_64_bytes);
