@@ -12,6 +12,7 @@
 #include "host_util.h"
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -31,6 +32,7 @@ struct GemmKernelParams {
   int rows_per_batch, batches, groups, N;
   int m_tiles_per_batch, n_tiles, total_tiles, k_blocks;
   int kb_per_tap, P;       // k-block -> (tap, column block); tap -> (parity, position offset)
+  int slab_stages, slab_stage_bytes, slab_chunk_bytes;   // SLAB kernels: ring depth / stage (= one tap of W) / chunk size
   int k16_last;            // K = 16 steps that hold data in the LAST k-block of a tap (1 .. 4): the columns beyond
                            // a_inner are zero padding (pos-conv at 80 channels per group: 64 + 16 of 128), and
                            // multiplying zeros cost 3 of every 8 MMAs there
@@ -60,10 +62,24 @@ constexpr bool epi_has_resid(int epi) { return epi == EPI_F32_RESID || epi == EP
 // with a 512-column accumulator had the tensor pipe idle 43 % of the time.  The row statistics are completed through
 // distributed shared memory (each warp writes its partial into both CTAs, one cluster-scope mbarrier per pass).
 constexpr bool epi_nsplit(int bn, int epi) { return epi == EPI_LN_GELU_BF16; }
+// Positional conv (the one user of EPI_F32_GELU_RESID): tap j of an output tile reads input rows [m0 + j, m0 + j + 128) -
+// the same rows as tap j - 1 shifted by one.  Fetching a 128-row A tile per tap moved 32 KB of A beside 20 KB of W per
+// tap and tile through L2 -> shared memory: 41 GB per launch at ~18 TB/s, the kernel's bound (tensor pipe 26 %).
+// SLAB: the 256 input rows [m0, m0 + 256) a tile can touch (128 + up to 128 taps) are fetched ONCE per tile into a
+// 128B-swizzled slab, and tap j's A operand is the slab read from row j on: descriptor start address + j * 128 bytes.
+// The start is then not aligned to the swizzle pattern's 1024-byte repeat; measured on B200, tap by tap: the tensor
+// core swizzles on ABSOLUTE shared-memory address bits (as TMA does when it writes the slab), so the descriptor's
+// matrix-base-offset field stays 0 - setting it to j mod 8 gives wrong products for every j not a multiple of 8.
+// The ring carries W alone.
+constexpr bool epi_slab(int epi) { return epi == EPI_F32_GELU_RESID; }
+constexpr int SLAB_ROWS = 256;
 
 template <int BN, int CG, int EPI>
 struct GemmCfg {
-  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr bool SLAB = epi_slab(EPI);
+  static constexpr int SLAB_CHUNK_BYTES = SLAB_ROWS * BK * 2;          // one 64-column chunk of the slab: 32 KB
+  static constexpr int SLAB_BYTES = SLAB ? 2 * SLAB_CHUNK_BYTES : 0;   // at most two chunks (a_inner <= 128)
+  static constexpr int A_BYTES = SLAB ? 0 : BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static_assert(BN <= 256, "a tile is one tcgen05.mma wide; the accumulator is double-buffered in TMEM");
@@ -79,9 +95,9 @@ struct GemmCfg {
   static constexpr int EPI_STAGE_BYTES = epi_has_resid(EPI) ? EPI_WARPS * 2 * RES_TILE_BYTES : EPI_WARPS * 32 * 20 * 4;
   static constexpr int EPI_PARAM_BYTES = 8192;  // per-warp bias slices [8][128] f32, or bias|gamma|beta [3][512] (LN)
   static constexpr int FIXED_BYTES = BAR_BYTES + EPI_STAGE_BYTES + EPI_PARAM_BYTES + 1024 /*align slack*/;
-  static constexpr int STAGES_RAW = (227 * 1024 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (227 * 1024 - FIXED_BYTES - SLAB_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static constexpr int SMEM_BYTES = SLAB_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 struct TileCoord {
@@ -112,13 +128,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* bar_base = smem + C::STAGES * C::STAGE_BYTES;
+  uint8_t* smem_al = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr bool SLAB = C::SLAB;
+  uint8_t* slab = smem_al;                       // [chunk][SLAB_ROWS][64] bf16, 128B swizzle (SLAB kernels only)
+  uint8_t* smem = smem_al + C::SLAB_BYTES;       // the TMA ring
+  // ring geometry: compile-time, except for the slab kernel whose stages hold only the W rows really fetched (80 of 128
+  // at the 1B width: eleven 10 KB stages instead of seven of 16 KB - the ring has to cover the TMA latency with half-taps
+  // of ~100 MMA cycles each)
+  const int NSTAGES = SLAB ? p.slab_stages : C::STAGES;
+  const int STAGE_B = SLAB ? p.slab_stage_bytes : C::STAGE_BYTES;
+  uint8_t* bar_base = smem + C::STAGES * C::STAGE_BYTES;   // the ring's region is sized at compile time either way
   uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
-  uint64_t* empty = full + C::STAGES;
-  uint64_t* tfull = empty + C::STAGES;
+  uint64_t* empty = full + NSTAGES;
+  uint64_t* tfull = empty + NSTAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* slab_full = tempty + 2;              // the tile's slab has landed / the tile's MMAs have read it
+  uint64_t* slab_empty = slab_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(slab_empty + 1);
   float* red1 = reinterpret_cast<float*>(bar_base + 256);  // [2][128] LN partial sums
   float* red2 = reinterpret_cast<float*>(bar_base + 2560); // [2][128]; N-split: red1 / red2 are [cta 2][half 2][128]
   uint64_t* ln_bar = reinterpret_cast<uint64_t*>(bar_base + 2304);   // N-split: [row quarter 4][pass 2]
@@ -135,7 +161,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
+    for (int s = 0; s < NSTAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -143,6 +169,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], EPI_WARPS * CG);  // the leader's barrier collects the epilogue warps of both CTAs
     }
+    mbar_init(slab_full, 1);
+    mbar_init(slab_empty, 1);
     if constexpr (epi_has_resid(EPI))
       for (int a = 0; a < EPI_WARPS * 2; ++a) mbar_init(&res_full[a], 1);
     if constexpr (NSPLIT)
@@ -171,13 +199,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // This single thread must issue one stage per ~512 MMA cycles: the loop carries its coordinates incrementally
       // (no division, nothing recomputed per k-block) - a 113-instruction body with two integer divisions measured
       // ~675 cycles per iteration and starved the tensor pipe (profiles/r1_notes.md).
+      uint32_t slab_it = 0;
       for (int tile = first_tile; tile < p.total_tiles; tile += tile_step) {
         const TileCoord t = decode_tile<CG>(p, tile, cta_rank);
         const int w_row = t.n_tile * BN + (CG == 2 ? cta_rank * p.b_box_rows : 0);
         int par = 0, pos = t.m0, c0 = 0, wk = 0;   // parity / position / column of the current tap, K offset in W
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        if constexpr (SLAB) {
+          // the tile's input rows, once: kb_per_tap chunks of [SLAB_ROWS][64]; rows / columns beyond the tensor read as 0
+          if (slab_it > 0) mbar_wait(slab_empty, (slab_it - 1) & 1);
+          mbar_arrive_expect_tx(slab_full, (uint32_t)p.kb_per_tap * C::SLAB_CHUNK_BYTES);
+          for (int ch = 0; ch < p.kb_per_tap; ++ch)
+            tma_load_5d(slab + ch * C::SLAB_CHUNK_BYTES, &tmA, slab_full, ch * BK, 0, t.m0, t.b, t.g);
+          ++slab_it;
+          // W: one ring stage per TAP (its kb_per_tap 64-column chunks behind one barrier): the issuing thread pays one
+          // barrier round trip and one commit per tap instead of two
+          const int n_taps = p.k_blocks / p.kb_per_tap;
+          for (int tap = 0; tap < n_taps; ++tap) {
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* sB = smem + s * STAGE_B;
+            mbar_arrive_expect_tx(&full[s], p.stage_tx_bytes * (uint32_t)p.kb_per_tap);
+            for (int ch = 0; ch < p.kb_per_tap; ++ch)
+              tma_load_3d(sB + ch * p.slab_chunk_bytes, &tmB, &full[s], wk + ch * BK, w_row, t.g);
+            wk += p.kb_per_tap * BK;
+            if (++s == NSTAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        } else for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* sA = smem + s * C::STAGE_BYTES;
+          uint8_t* sA = smem + s * STAGE_B;
           uint8_t* sB = sA + C::A_BYTES;
           if constexpr (CG == 2) {
             // both CTAs' bytes are credited to the leader's barrier, which the leader arms for the pair
@@ -199,7 +250,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               ++pos;
             }
           }
-          if (++s == C::STAGES) {
+          if (++s == NSTAGES) {
             s = 0;
             ph ^= 1;
           }
@@ -215,6 +266,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t idesc = make_idesc_bf16(BM * CG, p.umma_n, 0, 0);
       constexpr uint32_t desc_hi = uint32_t(1024 >> 4) | (1u << 14) | (uint32_t(SWZ_128B) << 29);  // SBO, v1, layout
       const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFF) >> 4) | (1u << 16);                      // LBO field = 1
+      const uint32_t slab_lo = ((smem_u32(slab) & 0x3FFFF) >> 4) | (1u << 16);
+      uint32_t slab_it = 0;
       int s = 0;
       uint32_t ph = 0;
       int as = 0;
@@ -223,11 +276,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        int kt = 0;   // k-block within the tap
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        int kt = 0;    // k-block within the tap
+        if constexpr (SLAB) {
+          mbar_wait(slab_full, slab_it & 1);
+          tc_fence_after();
+          const int n_taps = p.k_blocks / p.kb_per_tap;
+          for (int tap = 0; tap < n_taps; ++tap) {   // tap = the row of the slab its A operand starts at
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t w_lo = smem_lo + s * (STAGE_B >> 4);
+            for (int ch = 0; ch < p.kb_per_tap; ++ch) {
+              const uint32_t a_lo = slab_lo + ch * (C::SLAB_CHUNK_BYTES >> 4) + tap * (128 >> 4);
+              const uint32_t b_lo = w_lo + ch * (p.slab_chunk_bytes >> 4);
+              const int k16 = ch + 1 == p.kb_per_tap ? p.k16_last : BK / UMMA_K;
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adesc = (uint64_t(desc_hi) << 32) | (a_lo + k * (UMMA_K * 2 >> 4));
+                const uint64_t bdesc = (uint64_t(desc_hi) << 32) | (b_lo + k * (UMMA_K * 2 >> 4));
+                if (issuer && k < k16) umma_ss(d_tmem, adesc, bdesc, idesc, (tap | ch | k) != 0 ? 1u : 0u);
+              }
+            }
+            if (issuer) umma_commit(&empty[s]);   // frees the W stage when these MMAs retire
+            if (++s == NSTAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+          }
+        }
+        if constexpr (!SLAB) for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_lo = smem_lo + s * (C::STAGE_BYTES >> 4);
+          const uint32_t a_lo = smem_lo + s * (STAGE_B >> 4);
           const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
           const int k16 = kt + 1 == p.kb_per_tap ? p.k16_last : BK / UMMA_K;   // warp-uniform
           if (++kt == p.kb_per_tap) kt = 0;
@@ -245,14 +324,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (issuer) {
             if constexpr (CG == 2) umma_commit_cg2(&empty[s], 3); else umma_commit(&empty[s]);
           }
-          if (++s == C::STAGES) {
+          if (++s == NSTAGES) {
             s = 0;
             ph ^= 1;
           }
         }
         if (issuer) {   // accumulator complete
           if constexpr (CG == 2) umma_commit_cg2(&tfull[as], 3); else umma_commit(&tfull[as]);
+          if constexpr (SLAB) umma_commit(slab_empty);   // ... and the slab has been read: the next tile's may land
         }
+        if constexpr (SLAB) ++slab_it;
         __syncwarp();
         as ^= 1;
         if (as == 0) aph ^= 1;
@@ -693,6 +774,11 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   p.umma_n = n_cap;
   p.b_box_rows = p.umma_n / CG;   // W rows one CTA fetches per MMA-N chunk
   p.stage_tx_bytes = (uint32_t)CG * (C::A_BYTES + (uint32_t)p.b_box_rows * BK * 2);
+  // slab kernel: a ring stage holds one TAP of W = kb_per_tap chunks of the rows actually fetched (80 of 128 at the 1B
+  // width), each chunk aligned to the 1024-byte swizzle repeat
+  p.slab_chunk_bytes = ((p.b_box_rows * BK * 2 + 1023) / 1024) * 1024;
+  p.slab_stage_bytes = p.slab_chunk_bytes * p.kb_per_tap;
+  p.slab_stages = C::SLAB ? std::min(12, (C::STAGES * C::STAGE_BYTES) / p.slab_stage_bytes) : 0;
   p.ldo = a.ldo;
   p.out_batch_rows = a.out_batch_rows > 0 ? a.out_batch_rows : a.rows_per_batch;
   p.out = a.out;
@@ -719,7 +805,7 @@ int launch_cg(const GemmArgs& a, cudaStream_t stream) {
   ka.strides[1] = pos_stride_b;
   ka.strides[2] = nz(a.a_batch_stride * 2, pos_stride_b * (uint64_t)a.a_positions);
   ka.strides[3] = nz(a.a_group_stride * 2, ka.strides[2] * (uint64_t)a.batches);
-  ka.box[0] = BK; ka.box[1] = 1; ka.box[2] = BM; ka.box[3] = 1; ka.box[4] = 1;
+  ka.box[0] = BK; ka.box[1] = 1; ka.box[2] = C::SLAB ? SLAB_ROWS : BM; ka.box[3] = 1; ka.box[4] = 1;
   // W: {taps*k_pad, N, groups}
   TmapKey kw{};
   kw.base = a.W;
@@ -851,6 +937,9 @@ int gemm_bf16_tcgen05(const GemmArgs& a, cudaStream_t stream) {
       return launch<256, EPI_F32_RESID>(a, stream);
     case EPI_F32_GELU_RESID:
       OASR_REQUIRE(a.resid != nullptr && a.N <= 128, "gemm: gelu+residual epilogue needs a residual and N <= 128");
+      // the slab kernel: a tile's taps read rows [m0, m0 + 128 + taps - 1) of ONE parity, at most two 64-column chunks
+      OASR_REQUIRE(a.P == 1 && a.taps + BM - 1 <= SLAB_ROWS && a.a_inner <= 2 * BK && (a.k_pad == 0 || a.k_pad <= 2 * BK),
+                   "gemm: gelu+residual (pos-conv) epilogue needs stride 1, at most 129 taps and at most 128 input channels per group");
       return launch<128, EPI_F32_GELU_RESID>(a, stream);
     case EPI_ARGMAX:
       OASR_REQUIRE(a.argmax != nullptr && a.bias != nullptr && a.groups == 1, "gemm: argmax buffer / bias missing");
