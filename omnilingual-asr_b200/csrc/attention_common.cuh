@@ -126,5 +126,32 @@ __device__ __forceinline__ void softmax_chunk(const uint32_t* v, int ncols, floa
   }
 }
 
+// The two halves of softmax_chunk for kernels that hold a whole key block in registers (attention_v7.cu): the
+// maximum of W scores, and P = 2^(s c - m_ref) -> pk / pair sums with NO reference check in front of the exponentials.
+template <int BASE, int W, bool MASKED>
+__device__ __forceinline__ float chunk_max(const uint32_t* v, int ncols) {
+  float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains
+#pragma unroll
+  for (int i = 0; i < W; ++i)
+    if (!MASKED || BASE + i < ncols) cm4[(i >> 1) & 3] = fmaxf(cm4[(i >> 1) & 3], __uint_as_float(v[i]));
+  return fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
+}
+template <int HD, int BASE, int W, bool MASKED, int PKN>
+__device__ __forceinline__ void exp_chunk(const uint32_t* v, int ncols, float c, float neg_ref, RowState<HD>& rs,
+                                          uint32_t (&pk)[PKN]) {
+  const float2 c2 = make_float2(c, c), nm2 = make_float2(neg_ref, neg_ref);
+#pragma unroll
+  for (int i = 0; i < W; i += 2) {
+    const float2 x = ffma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), c2, nm2);
+    float p0 = ex2(x.x), p1 = ex2(x.y);
+    if (MASKED) {
+      if (BASE + i >= ncols) p0 = 0.f;
+      if (BASE + i + 1 >= ncols) p1 = 0.f;
+    }
+    rs.sm[(i >> 1) & 1] = fadd2(rs.sm[(i >> 1) & 1], make_float2(p0, p1));
+    pk[(BASE + i) >> 1] = pack_bf16x2(p0, p1);
+  }
+}
+
 }  // namespace att
 }  // namespace oasr

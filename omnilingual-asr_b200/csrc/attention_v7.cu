@@ -15,6 +15,7 @@
 
 #include <cstdlib>
 #include <map>
+#include <type_traits>
 #include <mutex>
 
 namespace oasr {
@@ -43,7 +44,7 @@ struct Attn7Params {
   __nv_bfloat16* out;
   long long* trace;   // debug: SM-clock timestamps of CTA (0,0,0), [role][event] (OASR_ATT_TRACE=file)
   int start_offset;   // tile X issues its first S this many cycles after tile X-1
-  int relay;          // exponential phases in relay (see the softmax warps): 0 off, n: hand on after n 16-column pieces
+  int relay;          // exponential phases in relay (see the softmax warps): 0 off, 1 / 2: hand on after the first / second 16-column piece
 };
 constexpr int TRACE_EVENTS = 256;   // per role: 0 MMA warp, 1 + X: first softmax warp of tile X
 // Tracing is a compile-time option (-DOASR_ATT_TRACING): even a never-taken stamp costs the softmax warps a branch,
@@ -374,8 +375,6 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
       for (int j = 0; j < nblk; ++j) {
         const int ncols = min(BKV, n_keys - j * BKV);  // valid keys in this block
         rs.j = j;
-        rs.sm[0] = make_float2(0.f, 0.f);
-        rs.sm[1] = make_float2(0.f, 0.f);
         uint32_t pk[BKV / 2];
         const bool tr = (warp & 3) == 0 && lane == 0;
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6);
@@ -397,32 +396,50 @@ attention_v7_kernel(const __grid_constant__ CUtensorMap tmq64, const __grid_cons
         // No tile can run two blocks ahead of its successor (its next start waits, around the ring, for the
         // successor's start), so a barrier generation never receives arrivals of two blocks.
         const uint32_t g_blk = gb + j;
-        if (p.relay > 0 && (X > 0 || g_blk > 0)) named_bar_sync(1 + (X + NT - 1) % NT, 256);
-        if (ncols == BKV) {
-          softmax_chunk<HD, 0, 16, false, BKV / 2>(va, ncols, c, rs, pk);
-          if (p.relay == 1) named_bar_arrive(1 + X, 256);
-          softmax_chunk<HD, 16, 16, false, BKV / 2>(va + 16, ncols, c, rs, pk);
-          if (p.relay >= 2) named_bar_arrive(1 + X, 256);
-          if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, false, BKV / 2>(vb, ncols, c, rs, pk);
-        } else {
-          softmax_chunk<HD, 0, 16, true, BKV / 2>(va, ncols, c, rs, pk);
-          if (p.relay == 1) named_bar_arrive(1 + X, 256);
-          softmax_chunk<HD, 16, 16, true, BKV / 2>(va + 16, ncols, c, rs, pk);
-          if (p.relay >= 2) named_bar_arrive(1 + X, 256);
-          if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 2);
-          if constexpr (VB > 0) softmax_chunk<HD, 32, VB, true, BKV / 2>(vb, ncols, c, rs, pk);
-        }
+        // The whole block is in registers, so nothing stands between the scores and their exponentials: no maximum, no
+        // vote.  (A per-chunk reference check put ~80 cycles of dependent latency - 4 FMNMX levels, FFMA, vote, branch -
+        // in front of each 16-column piece.)  The check comes AFTERWARDS, on the block's sum: a P above 2^REF_MARGIN
+        // (+inf included) makes the sum exceed it, and then - a few times per row at most, usually never - the
+        // reference moves by the exact power of two the block's maximum asks for and the block is computed again.
+        auto block = [&](auto masked_tag) {
+          constexpr bool MASKED = decltype(masked_tag)::value;
+          auto block_max = [&]() {
+            float cm = fmaxf(chunk_max<0, 16, MASKED>(va, ncols), chunk_max<16, 16, MASKED>(va + 16, ncols));
+            if constexpr (VB > 0) cm = fmaxf(cm, chunk_max<32, VB, MASKED>(vb, ncols));
+            return cm;
+          };
+          if (j == 0) rs.m_ref = ceilf(block_max() * c);   // column 0 is always a valid key
+          if (p.relay > 0 && (X > 0 || g_blk > 0)) named_bar_sync(1 + (X + NT - 1) % NT, 256);
+#pragma unroll 1
+          for (int pass = 0;; ++pass) {
+            rs.sm[0] = make_float2(0.f, 0.f);
+            rs.sm[1] = make_float2(0.f, 0.f);
+            // The relay hand-over sits between 16-column pieces, behind a run-time condition.  Where it lands in the
+            // instruction stream is ptxas's choice (SASS of this build: after ~7 / ~25 of the block's 48 MUFUs for
+            // relay 1 / 2), and the kernel time follows that placement: see profiles/r2_notes.md for the variants
+            // that tried to control it (compile-time position, data-dependent barrier number, phases cut by loops).
+            const float neg_ref = -rs.m_ref;
+            exp_chunk<HD, 0, 16, MASKED, BKV / 2>(va, ncols, c, neg_ref, rs, pk);
+            if (p.relay == 1 && pass == 0) named_bar_arrive(1 + X, 256);
+            exp_chunk<HD, 16, 16, MASKED, BKV / 2>(va + 16, ncols, c, neg_ref, rs, pk);
+            if (p.relay >= 2 && pass == 0) named_bar_arrive(1 + X, 256);
+            if constexpr (VB > 0) exp_chunk<HD, 32, VB, MASKED, BKV / 2>(vb, ncols, c, neg_ref, rs, pk);
+            const float2 t = fadd2(rs.sm[0], rs.sm[1]);
+            const float bs = t.x + t.y;
+            if (pass > 0 || !__any_sync(0xffffffffu, !(bs <= 0x1p80f))) {
+              rs.sum += bs;
+              break;
+            }
+            move_reference<HD, 0>(fmaf(block_max(), c, -rs.m_ref), rs, pk);
+          }
+        };
+        if (ncols == BKV) block(std::false_type{}); else block(std::true_type{});
         if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 4);
         // S(j+1) was issued when s_free(j) arrived, i.e. long ago: its chunks are requested now so that the TMEM read
         // latency hides under the P hand-off below
         if (j + 1 < nblk) {
           request_s(gb + j + 1);
           if (tr) ATT_TRACE(1 + X, (gb + j) * 6 + 3);
-        }
-        {
-          const float2 t = fadd2(rs.sm[0], rs.sm[1]);
-          rs.sum += t.x + t.y;
         }
         // The P buffer is free once P.V_X(j-1) has retired.  S_X(j+1) was issued after P.V_X(j-1) by the same thread
         // and tcgen05.commit covers every earlier MMA, so the s_full(j+1) wait above already implies it; only the
@@ -579,8 +596,8 @@ int attention_bf16_v7(const void* qkv, void* out, const int* n_frames, int B, in
   p.trace = nullptr;
   p.start_offset = START_OFFSET_CYCLES;
   static const int relay = [] {
-    const char* e = std::getenv("OASR_ATT_RELAY");   // 0: free-running tiles; 1 / 2: hand on after 16 / 32 columns
-    return e != nullptr ? std::atoi(e) : 1;
+    const char* e = std::getenv("OASR_ATT_RELAY");   // 0: free-running tiles; 1 / 2: hand on after the first / second 16-column piece
+    return e != nullptr ? std::atoi(e) : 2;
   }();
   p.relay = NT == 1 ? 0 : (relay < 0 ? 0 : (relay > 2 ? 2 : relay));   // one tile: nobody to take turns with
   const char* trace_path = std::getenv("OASR_ATT_TRACE");
