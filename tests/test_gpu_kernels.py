@@ -241,19 +241,22 @@ def test_attention(device, gen, H, hd, T, B, ragged):
     assert rel_err(o[0], ref2[0]) < 1e-2
 
 
-@pytest.mark.parametrize("hd,top", [(64, 6.0), (64, 30.0), (80, 30.0), (128, 24.0)])
-def test_attention_growing_scores_take_the_rescale_path(device, gen, hd, top):
+@pytest.mark.parametrize("hd,top,H,T,B", [(64, 6.0, 2, 700, 1), (64, 30.0, 2, 700, 1), (80, 30.0, 2, 700, 1),
+                                          (128, 24.0, 2, 700, 1),
+                                          # >= 148 work items: the three-tile shape with its relay (a block that is
+                                          # computed twice must hand over only once)
+                                          (80, 30.0, 16, 500, 5)])
+def test_attention_growing_scores_take_the_rescale_path(device, gen, hd, top, H, T, B):
     """Keys whose scores grow along the sequence push the running reference up several times (top = 30: by far more
     than the 2^80 margin, within a block and across blocks)."""
-    H, T, B = 2, 700, 1
     d = H * hd
     qkv = _rand((B * T, 3 * d), gen, 0.5)
-    ramp = torch.linspace(0.0, top, T, device=device)
+    ramp = torch.linspace(0.0, top, T, device=device).repeat(B)
     qkv[:, :d] = 1.0 + 0.1 * qkv[:, :d]                       # q ~ all ones
     qkv[:, d:2 * d] = ramp[:, None] + 0.1 * qkv[:, d:2 * d]   # k grows with the position
     qkv = qkv.bfloat16()
     out = torch.zeros((B * T, d), dtype=torch.bfloat16, device=device)
-    nfd = torch.tensor([T], dtype=torch.int32, device=device)
+    nfd = torch.tensor([T] * B, dtype=torch.int32, device=device)
     scale = hd ** -0.5
     N.check(lib().oasr_attention(N.ptr(qkv), N.ptr(out), N.ptr(nfd), B, T, H, hd, scale, N.stream_ptr()), "attention")
     sync()
@@ -329,11 +332,13 @@ def _attention_variant(tmp_path, env, B, T, H, hd):
 
 
 def test_attention_relay_switch(device, tmp_path):
-    """OASR_ATT_RELAY (exponential phases of the tiles kept apart by named barriers: 0 free-running, 1 default, 2):
+    """OASR_ATT_RELAY (exponential phases of the tiles kept apart by named barriers: 0 free-running, 1, 2 default):
     scheduling only - the outputs are bit-identical."""
-    ref = _attention_variant(tmp_path, {"OASR_ATT_RELAY": "0"}, 3, 700, 4, 80)
+    # 5 windows x 16 heads x 2 query triples = 160 work items: at least one per SM, so the three-tile shape (the one with
+    # a relay) runs, not the one-tile shape of small batches
+    ref = _attention_variant(tmp_path, {"OASR_ATT_RELAY": "0"}, 5, 500, 16, 80)
     for r in ("1", "2"):
-        assert (_attention_variant(tmp_path, {"OASR_ATT_RELAY": r}, 3, 700, 4, 80) == ref).all()
+        assert (_attention_variant(tmp_path, {"OASR_ATT_RELAY": r}, 5, 500, 16, 80) == ref).all()
 
 
 def test_attention_env_switch_v4(device, tmp_path):
